@@ -1,0 +1,125 @@
+// The device-operation interface the host-side solver logic (engine.cpp) is written against.
+//
+// The shipped library has exactly ONE implementation: CudaOps (cuda_ops.cu, sm_100a kernels).
+// The interface exists so that the scalar control flow of the solver (Newton, Armijo, Eisenstat-
+// Walker, LGMRES bookkeeping) can be unit-tested in the GPU-less build container against SciPy
+// with a CPU test double that lives under tests/hostsim/ and is never part of the product.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "hd_math.h"
+
+namespace jfnk {
+
+// A scalar that is only known on the device at enqueue time:
+//   value = mult * S[mul_idx] * sqrt(S[mul_sqrt_idx]) / sqrt(S[div_sqrt_idx])    (index < 0: factor 1)
+struct ScalarRef {
+  double mult;
+  int mul_idx;
+  int mul_sqrt_idx;
+  int div_sqrt_idx;
+};
+inline ScalarRef sref(double mult, int mul_idx = -1, int mul_sqrt_idx = -1, int div_sqrt_idx = -1) {
+  ScalarRef r; r.mult = mult; r.mul_idx = mul_idx; r.mul_sqrt_idx = mul_sqrt_idx; r.div_sqrt_idx = div_sqrt_idx; return r;
+}
+JF_HD double eval_sref(const double* S, const ScalarRef& r) {
+  double v = r.mult;
+  if (r.mul_idx >= 0) v *= S[r.mul_idx];
+  if (r.mul_sqrt_idx >= 0) v *= sqrt(S[r.mul_sqrt_idx]);
+  if (r.div_sqrt_idx >= 0) v /= sqrt(S[r.div_sqrt_idx]);
+  return v;
+}
+
+struct Grid {
+  int nx, ny;      // global grid: ny rows x nx columns
+  int row0, nrows; // local slab of rows
+  int rank, nranks;
+  size_t n() const { return (size_t)nx * (size_t)nrows; }
+  size_t n_global() const { return (size_t)nx * (size_t)ny; }
+};
+
+// Mesh geometry / parameters of the moving-mesh problems (PMA2_nk.py:23-40, droplet.py:23-53).
+struct MeshParams {
+  double dksi, deta;
+  double bl, br, bb, bt; // Dirichlet values of Q_ksi (left,right) and Q_eta (bottom,top)
+};
+struct Pma2Params { double lambd, beta, epsilon; int m; double dt; };
+struct DropletParams { double epsilon; int n_exp, m_exp; double Bo, alpha2, epsilon2; double dt; };
+
+class DeviceOps {
+ public:
+  virtual ~DeviceOps() {}
+  virtual int64_t launches() const = 0;
+  // 0 when no asynchronous device error is pending, else JFNK_CUDA_ERROR / JFNK_NCCL_ERROR (message via last_error()).
+  virtual int status() = 0;
+  virtual const char* last_error() const = 0;
+
+  // ---- scalar arena ---------------------------------------------------------------------------
+  virtual void read_scalars(int off, int cnt, double* host) = 0; // synchronises the stream
+  virtual void write_scalars(int off, int cnt, const double* host) = 0;
+  virtual void allreduce_sum(int off, int cnt) = 0; // across slab ranks; no-op on one rank
+  virtual void allreduce_max(int off, int cnt) = 0;
+
+  // ---- BLAS-1 on slab-local vectors of length grid.n() -------------------------------------------
+  // out[i] = V_i . w (i < nv), out[nv] = w . w.   guard != 0: skip unless gs_second_pass_taken(S, nv, tau2).
+  virtual void mdot(int nv, const double* const* V, const double* w, int out_off, int guard, double tau2) = 0;
+  // w -= sum_i (S[rd_off+i] / S[JS_VN2+i]) V_i ; S[n2_off] = ||w||^2.  guard as above.
+  virtual void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int guard, double tau2) = 0;
+  // w -= sum_i S[JS_COEF+i] V_i ; S[n2_off] = ||w||^2   (public microbenchmark form)
+  virtual void maxpy_sub(int nv, const double* const* V, double* w, int n2_off) = 0;
+  // out = sum_i S[JS_COEF+i] Z_i ; S[n2_off] = ||out||^2
+  virtual void maxpy(int nz, const double* const* Z, double* out, int n2_off) = 0;
+  // out = a x + b y (y may be null; out may alias x or y) ; S[n2_off] = ||out||^2 when n2_off >= 0
+  virtual void lincomb(double* out, ScalarRef a, const double* x, ScalarRef b, const double* y, int n2_off) = 0;
+  // out = (x - y)/div
+  virtual void diff_scale(double* out, const double* x, const double* y, ScalarRef div) = 0;
+  virtual void copy(double* dst, const double* src) = 0;
+  virtual void maxabs(const double* v, int out_off) = 0;
+  // Hessenberg column + Givens update of Arnoldi step j; LSQ back-substitution (hd_math.h).
+  virtual void givens(int j, int pass2, double tau2) = 0;
+  virtual void lsq(int nit, const int* zn2_idx, int scale_n2_idx) = 0;
+
+  // ---- Swift-Hohenberg stencil operators --------------------------------------------------------
+  virtual void sh_setup(const SHParams& p) = 0;
+  virtual void sh_spmv(int which, const double* x, double* y) = 0; // 0: Lap (5-pt), 1: L (13-pt)
+  virtual void sh_set_prev(const double* uo, double* d) = 0;       // d = Uo/k + N(Uo)/2
+  // t = x + a v (v may be null) ; F = G(t) - d ; xt_out (may be null) = t ;
+  // S[norm_off+0] = sum F^2, S[norm_off+1] = max|F|, S[norm_off+2] = max|t|  (local partials; caller all-reduces)
+  virtual void sh_residual(const double* x, const double* v, ScalarRef a, const double* d, double* xt_out, double* F,
+                           int norm_off) = 0;
+  // cache the row halos of the linearisation point (multi-rank); no-op on one rank
+  virtual void sh_bind_x0(const double* x0) = 0;
+  // w = (G(x0 + sc z) - d - f0)/div
+  virtual void sh_jvp(const double* x0, const double* z, ScalarRef sc, ScalarRef div, const double* d, const double* f0,
+                      double* w) = 0;
+  // linearly-implicit SH: D = (5U-Uo)^2 k/16 - g k U ; b = U + k/2 L U
+  virtual void shlin_prepare(const double* U, const double* Uo, double* D, double* b) = 0;
+  // w = a (z + D z - k/2 L z)
+  virtual void shlin_matvec(const double* z, ScalarRef a, const double* D, double* w) = 0;
+
+  // ---- moving-mesh operators (PMA2 / droplet) ----------------------------------------------------
+  // Q -> metric fields M[0..6] = Q_ksiksi, Q_etaeta, Q_ksieta, J, A11, A22, A12 (each grid.n() long)
+  virtual void mesh_metrics(const MeshParams& mp, const double* Q, double* const* M) = 0;
+  // (v_xx, v_yy) = Laplace_operator(v); `sum_only`: vxx receives v_xx + v_yy and vyy is ignored
+  // deriv_bc = 1: the first derivatives of v fed to the cross terms are boundary-zeroed the way
+  // droplet.py:719-722 does it (v_ksi = 0 on left/right/bottom edges, v_eta = 0 on the top edge).
+  virtual void mesh_laplace(const MeshParams& mp, const double* const* M, const double* v, double* vxx, double* vyy,
+                            int sum_only, int deriv_bc) = 0;
+  // PMA2 rhs(u) given lap2 = Laplace(Laplace(u)):  out = -lambd/(1+u)^2 + lambd eps^(m-2)/(1+u)^m - beta^2 lap2, boundary -> 0
+  virtual void pma2_rhs(const Pma2Params& pp, const double* u, const double* lap2, double* out) = 0;
+  // F = (u - uval)/dt - (rhs + cn)/2 ; norms as sh_residual (max|t| is max|u|)
+  virtual void pma2_combine(const Pma2Params& pp, const double* u, const double* uval, const double* rhs,
+                            const double* cn, double* F, int norm_off) = 0;
+  // droplet: p = -(lap) + PI(h) + Bo cos(alpha2) h
+  virtual void droplet_pressure(const DropletParams& dp, const double* h, const double* lap, double* p) = 0;
+  // (A, B) = flux components from pressure p and height h  (droplet.py:439-447)
+  virtual void droplet_flux(const MeshParams& mp, const DropletParams& dp, const double* const* M, const double* p,
+                            const double* h, double* A, double* B) = 0;
+  // out = (Q_etaeta D_ksi A - Q_ksieta D_eta A - Q_ksieta D_ksi B + Q_ksiksi D_eta B)/J   (droplet.py:448-449)
+  virtual void droplet_div(const MeshParams& mp, const double* const* M, const double* A, const double* B, double* out) = 0;
+  // F = (u - uval) - dt (F2 + Fprev)/2 ; norms as sh_residual
+  virtual void droplet_combine(const DropletParams& dp, const double* u, const double* uval, const double* F2,
+                               const double* Fprev, double* F, int norm_off) = 0;
+};
+
+} // namespace jfnk

@@ -1,0 +1,231 @@
+// Matrix-free 4th-order finite differences on the non-periodic computational (ksi, eta) grid of the
+// moving-mesh problems, shared verbatim by the CUDA kernels and the CPU test double.
+//
+// Reference: make_M (PMA2_nk.py:181-233, droplet.py:778-833) builds these operators as sparse
+// matrices with kron(); here every row of those matrices is applied on the fly:
+//   D1  first derivative  [1,-8,0,8,-1]/(12h),   one-sided closures rows 0,1,n-2,n-1 (droplet.py:801-804)
+//   D2  second derivative [-1,16,-30,16,-1]/(12h^2), closures rows 0,1,n-2,n-1      (droplet.py:785-790)
+//   Dxy = D1(eta) (x) D1(ksi)                                                        (droplet.py:810)
+// Layout: flat index = row*nx + col, row = eta index (0 = bottom edge), col = ksi index (0 = left edge).
+#pragma once
+#include "device_ops.h"
+
+namespace jfnk {
+
+struct MeshGeom {
+  int nx, ny;
+  double dksi, deta, dksi2, deta2;
+  double bl, br, bb, bt;
+  double d1x[5][5], d1y[5][5]; // [row type][k] weights, already divided by 12h
+  double d2x[5][6], d2y[5][6]; // [row type][k] weights, already divided by 12h^2
+};
+
+// row type of index i in a dimension of n points: 0,1 = first two rows, 3,4 = last two rows, 2 = interior
+JF_HD int fd_type(int i, int n) { return i == 0 ? 0 : (i == 1 ? 1 : (i == n - 2 ? 3 : (i == n - 1 ? 4 : 2))); }
+// first column touched by the 5-wide D1 row / the 6-wide D2 row
+JF_HD int d1_start(int i, int n, int type) { return type < 2 ? 0 : (type > 2 ? n - 5 : i - 2); }
+JF_HD int d2_start(int i, int n, int type) { return type < 2 ? 0 : (type > 2 ? n - 6 : i - 2); }
+JF_HD int d2_count(int type) { return type == 2 ? 5 : 6; }
+
+inline MeshGeom make_geom(const MeshParams& mp, int nx, int ny) {
+  MeshGeom g;
+  g.nx = nx; g.ny = ny;
+  g.dksi = mp.dksi; g.deta = mp.deta; g.dksi2 = mp.dksi * mp.dksi; g.deta2 = mp.deta * mp.deta;
+  g.bl = mp.bl; g.br = mp.br; g.bb = mp.bb; g.bt = mp.bt;
+  const double c1[5][5] = {{-25, 48, -36, 16, -3}, {-3, -10, 18, -6, 1}, {1, -8, 0, 8, -1}, {-1, 6, -18, 10, 3}, {3, -16, 36, -48, 25}};
+  const double c2[5][6] = {{-415.0 / 6, 96, -36, 32.0 / 3, -1.5, 0}, {10, -15, -4, 14, -6, 1}, {-1, 16, -30, 16, -1, 0},
+                           {1, -6, 14, -4, -15, 10}, {0, -1.5, 32.0 / 3, -36, 96, -415.0 / 6}};
+  for (int t = 0; t < 5; ++t) {
+    for (int k = 0; k < 5; ++k) { g.d1x[t][k] = c1[t][k] / (12 * g.dksi); g.d1y[t][k] = c1[t][k] / (12 * g.deta); }
+    for (int k = 0; k < 6; ++k) { g.d2x[t][k] = c2[t][k] / (12 * g.dksi2); g.d2y[t][k] = c2[t][k] / (12 * g.deta2); }
+  }
+  return g;
+}
+
+// ---- plain derivatives -------------------------------------------------------------------------
+JF_HD double d_ksi(const MeshGeom& g, const double* f, int r, int c) {
+  int t = fd_type(c, g.nx), s = d1_start(c, g.nx, t);
+  const double* p = f + (size_t)r * g.nx + s;
+  const double* w = g.d1x[t];
+  return w[0] * p[0] + w[1] * p[1] + w[2] * p[2] + w[3] * p[3] + w[4] * p[4];
+}
+JF_HD double d_eta(const MeshGeom& g, const double* f, int r, int c) {
+  int t = fd_type(r, g.ny), s = d1_start(r, g.ny, t);
+  const double* p = f + (size_t)s * g.nx + c;
+  const double* w = g.d1y[t];
+  size_t n = g.nx;
+  return w[0] * p[0] + w[1] * p[n] + w[2] * p[2 * n] + w[3] * p[3 * n] + w[4] * p[4 * n];
+}
+JF_HD double d2_ksi(const MeshGeom& g, const double* f, int r, int c) {
+  int t = fd_type(c, g.nx), s = d2_start(c, g.nx, t), cnt = d2_count(t);
+  const double* w = g.d2x[t];
+  if (t == 4) { s += 1; w += 1; cnt = 5; } // last row touches only the last 5 columns
+  const double* p = f + (size_t)r * g.nx + s;
+  double acc = 0.0;
+  for (int k = 0; k < cnt; ++k) acc += w[k] * p[k];
+  return acc;
+}
+JF_HD double d2_eta(const MeshGeom& g, const double* f, int r, int c) {
+  int t = fd_type(r, g.ny), s = d2_start(r, g.ny, t), cnt = d2_count(t);
+  const double* w = g.d2y[t];
+  if (t == 4) { s += 1; w += 1; cnt = 5; }
+  const double* p = f + (size_t)s * g.nx + c;
+  double acc = 0.0;
+  for (int k = 0; k < cnt; ++k) acc += w[k] * p[(size_t)k * g.nx];
+  return acc;
+}
+// kron(D1 eta, D1 ksi) f
+JF_HD double d_ksieta(const MeshGeom& g, const double* f, int r, int c) {
+  int ty = fd_type(r, g.ny), sy = d1_start(r, g.ny, ty);
+  int tx = fd_type(c, g.nx), sx = d1_start(c, g.nx, tx);
+  const double* wy = g.d1y[ty];
+  const double* wx = g.d1x[tx];
+  double acc = 0.0;
+  for (int a = 0; a < 5; ++a) {
+    const double* p = f + (size_t)(sy + a) * g.nx + sx;
+    for (int b = 0; b < 5; ++b) acc += (wy[a] * wx[b]) * p[b];
+  }
+  return acc;
+}
+
+// ---- mesh metric fields (compute_Q_spatial_ders + J + the A_ij of Laplace_operator) -------------
+// PMA2_nk.py:235-248,87,275-277 ; droplet.py:696-711,376,613-615.
+// M[0..6] = Q_ksiksi, Q_etaeta, Q_ksieta, J, A11, A22, A12
+JF_HD void mesh_metrics_point(const MeshGeom& g, const double* Q, int r, int c, double* const* M) {
+  size_t e = (size_t)r * g.nx + c;
+  double qxx = d2_ksi(g, Q, r, c);
+  if (c == 0) qxx += 25.0 / (6.0 * g.dksi) * fabs(g.bl);
+  if (c == g.nx - 1) qxx += 25.0 / (6.0 * g.dksi) * fabs(g.br);
+  double qyy = d2_eta(g, Q, r, c);
+  if (r == g.ny - 1) qyy += 25.0 / (6.0 * g.deta) * fabs(g.bt);
+  if (r == 0) qyy += 25.0 / (6.0 * g.deta) * fabs(g.bb);
+  bool bdy = (r == 0 || c == 0 || r == g.ny - 1 || c == g.nx - 1);
+  double qxy = bdy ? 0.0 : d_ksieta(g, Q, r, c);
+  double J = qxx * qyy - qxy * qxy;
+  M[0][e] = qxx; M[1][e] = qyy; M[2][e] = qxy; M[3][e] = J;
+  M[4][e] = (qxy * qxy + qyy * qyy) / J;
+  M[5][e] = (qxy * qxy + qxx * qxx) / J;
+  M[6][e] = -(qxy * (qxx + qyy)) / J;
+}
+
+// ---- Laplace_operator (PMA2_nk.py:263-343, droplet.py:601-681) ---------------------------------
+// conservative (A v')' along one grid line: A, v sampled at stride `st`, i = index along the line, n = line length
+JF_HD double cons_line(const double* A, const double* v, size_t st, int i, int n, double h2) {
+#define A_(k) A[(size_t)(k) * st]
+#define V_(k) v[(size_t)(k) * st]
+  if (i == 0 || i == n - 1) return 0.0; // boundary columns stay 0
+  if (i == 1)
+    return A_(1) * (10 * V_(0) - 15 * V_(1) - 4 * V_(2) + 14 * V_(3) - 6 * V_(4) + V_(5)) / (12 * h2) +
+           (-3 * V_(0) - 10 * V_(1) + 18 * V_(2) - 6 * V_(3) + V_(4)) *
+               (-3 * A_(0) - 10 * A_(1) + 18 * A_(2) - 6 * A_(3) + A_(4)) / (144 * h2);
+  if (i == 2)
+    return A_(2) * (-V_(0) + 16 * V_(1) - 30 * V_(2) + 16 * V_(3) - V_(4)) / (12 * h2) +
+           (V_(0) - 8 * V_(1) + 8 * V_(3) - V_(4)) * (A_(0) - 8 * A_(1) + 8 * A_(3) - A_(4)) / (144 * h2);
+  int m = n - 1;
+  if (i == n - 2)
+    return A_(m - 1) * (10 * V_(m) - 15 * V_(m - 1) - 4 * V_(m - 2) + 14 * V_(m - 3) - 6 * V_(m - 4) + V_(m - 5)) / (12 * h2) +
+           (3 * V_(m) + 10 * V_(m - 1) - 18 * V_(m - 2) + 6 * V_(m - 3) - V_(m - 4)) *
+               (3 * A_(m) + 10 * A_(m - 1) - 18 * A_(m - 2) + 6 * A_(m - 3) - A_(m - 4)) / (144 * h2);
+  if (i == n - 3)
+    return A_(m - 2) * (-V_(m) + 16 * V_(m - 1) - 30 * V_(m - 2) + 16 * V_(m - 3) - V_(m - 4)) / (12 * h2) +
+           (V_(m - 4) - 8 * V_(m - 3) + 8 * V_(m - 1) - V_(m)) * (A_(m - 4) - 8 * A_(m - 3) + 8 * A_(m - 1) - A_(m)) / (144 * h2);
+  return (4 * (A_(i - 1) * (V_(i - 3) - 8 * V_(i - 2) + 8 * V_(i) - V_(i + 1))) -
+          (-A_(i - 2) + 9 * A_(i - 1) + 9 * A_(i) - A_(i + 1)) * (V_(i - 2) - 27 * V_(i - 1) + 27 * V_(i) - V_(i + 1)) +
+          (-A_(i - 1) + 9 * A_(i) + 9 * A_(i + 1) - A_(i + 2)) * (V_(i - 1) - 27 * V_(i) + 27 * V_(i + 1) - V_(i + 2)) -
+          4 * (A_(i + 1) * (V_(i - 1) - 8 * V_(i) + 8 * V_(i + 2) - V_(i + 3)))) /
+         (288 * h2);
+#undef A_
+#undef V_
+}
+
+// first derivatives of v as Laplace_operator's callers pass them in.  deriv_bc = 1 reproduces
+// compute_u_spatial_ders of droplet.py:719-722 (incl. its `U_dksi[Ibdy.Bottom] = 0` line).
+JF_HD double v_ksi_bc(const MeshGeom& g, const double* v, int r, int c, int deriv_bc) {
+  if (deriv_bc && (c == 0 || c == g.nx - 1 || r == 0)) return 0.0;
+  return d_ksi(g, v, r, c);
+}
+JF_HD double v_eta_bc(const MeshGeom& g, const double* v, int r, int c, int deriv_bc) {
+  if (deriv_bc && r == g.ny - 1) return 0.0;
+  return d_eta(g, v, r, c);
+}
+
+JF_HD void mesh_laplace_point(const MeshGeom& g, const double* const* M, const double* v, int r, int c, int deriv_bc,
+                              double& vxx, double& vyy) {
+  const double* J = M[3];
+  const double* A11 = M[4];
+  const double* A22 = M[5];
+  const double* A12 = M[6];
+  size_t e = (size_t)r * g.nx + c;
+  // B.1: (A11 v_ksi)_ksi along the row, (A22 v_eta)_eta along the column
+  double xx = cons_line(A11 + (size_t)r * g.nx, v + (size_t)r * g.nx, 1, c, g.nx, g.dksi2);
+  double yy = cons_line(A22 + c, v + c, (size_t)g.nx, r, g.ny, g.deta2);
+  // B.2: D_ksi(A12 v_eta) with left/right columns zeroed ; D_eta(A12 v_ksi) with top/bottom rows zeroed
+  if (c != 0 && c != g.nx - 1) {
+    int t = fd_type(c, g.nx), s = d1_start(c, g.nx, t);
+    const double* w = g.d1x[t];
+    double acc = 0.0;
+    for (int k = 0; k < 5; ++k) {
+      if (w[k] == 0.0) continue;
+      int cc = s + k;
+      acc += w[k] * (A12[(size_t)r * g.nx + cc] * v_eta_bc(g, v, r, cc, deriv_bc));
+    }
+    xx += acc;
+  }
+  if (r != 0 && r != g.ny - 1) {
+    int t = fd_type(r, g.ny), s = d1_start(r, g.ny, t);
+    const double* w = g.d1y[t];
+    double acc = 0.0;
+    for (int k = 0; k < 5; ++k) {
+      if (w[k] == 0.0) continue;
+      int rr = s + k;
+      acc += w[k] * (A12[(size_t)rr * g.nx + c] * v_ksi_bc(g, v, rr, c, deriv_bc));
+    }
+    yy += acc;
+  }
+  vxx = xx / J[e];
+  vyy = yy / J[e];
+}
+
+// ---- PMA2 pointwise (PMA2_nk.py:131,139,157-159 ; :410-418) -------------------------------------
+JF_HD double pma2_rhs_point(const Pma2Params& p, double u, double lap2) {
+  double q = 1.0 + u;
+  double rhs = -p.lambd / (q * q);
+  if (p.epsilon != 0.0) rhs += p.lambd * pow(p.epsilon, (double)(p.m - 2)) / pow(q, (double)p.m);
+  rhs -= p.beta * p.beta * lap2;
+  return rhs;
+}
+JF_HD double pma2_combine_point(const Pma2Params& p, double u, double uval, double rhs, double cn) {
+  return (u - uval) / p.dt - (rhs + cn) / 2.0;
+}
+
+// ---- droplet pointwise (droplet.py:435-473) -------------------------------------------------------
+JF_HD double ipow(double x, int n) { double r = 1.0; for (int i = 0; i < n; ++i) r *= x; return r; }
+JF_HD double droplet_PI(const DropletParams& p, double h) {
+  double q = p.epsilon / h;
+  return (p.n_exp - 1) * (p.m_exp - 1) * (ipow(q, p.m_exp) - ipow(q, p.n_exp)) / (2 * p.epsilon * (p.n_exp - p.m_exp));
+}
+JF_HD double droplet_pressure_point(const DropletParams& p, double h, double lap) {
+  return -lap + droplet_PI(p, h) + p.Bo * cos(p.alpha2) * h;
+}
+JF_HD void droplet_flux_point(const MeshGeom& g, const DropletParams& dp, const double* const* M, const double* p,
+                              const double* h, int r, int c, double& A, double& B) {
+  size_t e = (size_t)r * g.nx + c;
+  double pk = (c == 0 || c == g.nx - 1) ? 0.0 : d_ksi(g, p, r, c);
+  double pe = (r == 0 || r == g.ny - 1) ? 0.0 : d_eta(g, p, r, c);
+  double qxx = M[0][e], qyy = M[1][e], qxy = M[2][e], J = M[3][e];
+  double pdx = (qyy * pk - qxy * pe) / J;
+  double pdy = (-qxy * pk + qxx * pe) / J;
+  double h3 = h[e] * h[e] * h[e];
+  A = (pdx - dp.Bo * sin(dp.alpha2) / dp.epsilon2) * h3 / 3.0;
+  B = pdy * h3 / 3.0;
+}
+JF_HD double droplet_div_point(const MeshGeom& g, const double* const* M, const double* A, const double* B, int r, int c) {
+  size_t e = (size_t)r * g.nx + c;
+  double qxx = M[0][e], qyy = M[1][e], qxy = M[2][e], J = M[3][e];
+  return (qyy * d_ksi(g, A, r, c) - qxy * d_eta(g, A, r, c) - qxy * d_ksi(g, B, r, c) + qxx * d_eta(g, B, r, c)) / J;
+}
+JF_HD double droplet_combine_point(const DropletParams& p, double u, double uval, double F2, double Fprev) {
+  return (u - uval) - p.dt * (F2 + Fprev) / 2.0;
+}
+
+} // namespace jfnk

@@ -1,0 +1,43 @@
+// Layout of the device-resident scalar arena (fp64) shared by all kernels of one context.
+//
+// Every reduction result (dots, squared norms, max-norms), the Hessenberg/Givens state of the
+// Arnoldi process and the LSQ solution live here, so that one Arnoldi step needs no host
+// round-trip except the single convergence scalar (JS_RES).  Norm slots hold SQUARED 2-norms
+// (raw sums) so that they can be all-reduced across ranks in place; consumers take the sqrt.
+#pragma once
+
+namespace jfnk {
+
+constexpr int JF_MAXV = 48;  // max basis vectors (inner_m + outer_k + 1 <= 48)
+constexpr int JF_MAXOV = 16; // max augmentation-vector ring slots (outer_k + 1 <= 16)
+
+enum ScalarSlot : int {
+  // residual norms, slot set A (current iterate) and B (line-search trial)
+  JS_F2_A = 0, JS_FMAX_A, JS_XMAX_A, JS_pad0,
+  JS_F2_B, JS_FMAX_B, JS_XMAX_B, JS_pad1,
+  JS_TMP0, JS_TMP1, JS_TMP2, JS_TMP3, // misc reductions (||v||^2 for the public jvp, ||dx||^2, ...)
+  JS_WW,   // w.w before orthogonalisation (alias of RD[nv], copied by givens)
+  JS_HN2A, // ||w||^2 after the first GS pass
+  JS_HN2B, // ||w||^2 after the second GS pass (or copy of HN2A when skipped)
+  JS_RES,  // |g_{j+1}|: GMRES residual estimate relative to ||v0|| = 1   -> host
+  JS_FLAGS, // bit0 breakdown, bit1 non-finite, bit2 second GS pass taken -> host
+  JS_DXN2, // ||dx||^2 of the assembled LGMRES correction
+  JS_pad2, JS_pad3,
+  JS_RD = 20,                 // [JF_MAXV+1] raw dots V_i.w ; RD[nv] = w.w
+  JS_RD2 = JS_RD + JF_MAXV + 1, // [JF_MAXV+1] second-pass raw dots
+  JS_VN2 = JS_RD2 + JF_MAXV + 1, // [JF_MAXV+1] squared norms of the (unnormalised) Arnoldi vectors
+  JS_ZN2 = JS_VN2 + JF_MAXV + 1, // [JF_MAXOV]  squared norms of the augmentation vectors (ring slots)
+  JS_COEF = JS_ZN2 + JF_MAXOV,   // [JF_MAXV]   coefficients for multi-axpy (GS update or dx assembly)
+  JS_CS = JS_COEF + JF_MAXV,     // [JF_MAXV]   Givens cosines
+  JS_SN = JS_CS + JF_MAXV,       // [JF_MAXV]   Givens sines
+  JS_G = JS_SN + JF_MAXV,        // [JF_MAXV+1] rotated right-hand side
+  JS_Y = JS_G + JF_MAXV + 1,     // [JF_MAXV]   LSQ solution
+  JS_R = JS_Y + JF_MAXV,         // [JF_MAXV*JF_MAXV] upper-triangular factor, column-major R[i + j*JF_MAXV]
+  JS_COUNT = JS_R + JF_MAXV * JF_MAXV
+};
+
+constexpr int JF_FLAG_BREAKDOWN = 1;
+constexpr int JF_FLAG_NONFINITE = 2;
+constexpr int JF_FLAG_REORTH = 4;
+
+} // namespace jfnk

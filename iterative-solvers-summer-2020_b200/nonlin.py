@@ -1,0 +1,94 @@
+"""``newton_krylov`` with SciPy's signature, running on the B200 engine.
+
+Drop-in for the reference's call sites
+    newton_krylov(residual, Uo, verbose=1)                                   sh_scipy_nk.py:61
+    newton_krylov(residual, U.val, verbose=0)                                PMA2_nk.py:100
+    newton_krylov(lambda u: residual(u, F, dt_n), U.val, verbose=1, maxiter=20, f_tol=1e-7)   droplet.py:383
+where ``F`` is a device residual handle (:mod:`residuals`) instead of a NumPy closure.  Return value,
+exceptions (``NoConvergence(x)``, ``ValueError``) and the verbose trace format follow
+scipy/optimize/_nonlin.py:134-277.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+
+from . import _capi
+from .context import Context, HistoryBuffer, NoConvergence  # noqa: F401
+from .residuals import _DeviceResidual
+
+
+def newton_krylov(F, xin, iter=None, rdiff=None, method="lgmres", inner_maxiter=20, inner_M=None, outer_k=10,
+                  verbose=False, maxiter=None, f_tol=None, f_rtol=None, x_tol=None, x_rtol=None, tol_norm=None,
+                  line_search="armijo", callback=None, full_output=False, raise_exception=True, **kw):
+    """Find a root of ``F`` with the Jacobian-free Newton-Krylov method (LGMRES inner solver).
+
+    Same parameters as :func:`scipy.optimize.newton_krylov`; the differences are
+      * ``F`` is a device residual handle (``SHResidual``, ``PMA2Residual``, ``DropletResidual``),
+      * ``method`` must be ``'lgmres'`` (the only inner solver the reference uses), ``inner_M`` must be None,
+        ``tol_norm`` must be None (max-norm),
+      * ``inner_maxiter`` is accepted and -- exactly as in SciPy for LGMRES -- has no effect
+        (KrylovJacobian overrides ``maxiter=1`` and LGMRES' ``inner_m`` stays 30, _nonlin.py:1503-1506);
+        pass ``inner_inner_m=...`` to change the Arnoldi length as SciPy's ``inner_*`` forwarding allows.
+    """
+    if not isinstance(F, _DeviceResidual):
+        raise TypeError("F must be a device residual handle (SHResidual, PMA2Residual, DropletResidual); "
+                        "there is no CPU path for arbitrary Python callables")
+    if method != "lgmres":
+        raise NotImplementedError("only method='lgmres' (the reference's inner solver) is implemented")
+    if inner_M is not None:
+        raise NotImplementedError("inner_M (preconditioning) is not used by the reference and not implemented")
+    if tol_norm is not None:
+        raise NotImplementedError("tol_norm: only the default max-norm is implemented")
+    inner_m = 30
+    for key, value in kw.items():
+        if not key.startswith("inner_"):
+            raise ValueError(f"Unknown parameter {key}")
+        if key == "inner_inner_m":
+            inner_m = int(value)
+        elif key == "inner_outer_k":
+            outer_k = int(value)
+        else:
+            raise NotImplementedError(f"inner option {key!r} is not supported by the device LGMRES")
+
+    ctx = F.context(inner_m=inner_m, outer_k=outer_k)
+    opts = Context.make_opts(f_tol=f_tol, f_rtol=f_rtol, x_tol=x_tol, x_rtol=x_rtol, rdiff=rdiff, maxiter=maxiter,
+                             iter=iter, line_search=line_search)
+    du = ctx.vec(xin, "xin")
+    hist = HistoryBuffer()
+
+    cb_c = None
+    if callback is not None:
+        n = ctx.n
+
+        def _cb(_user, _it, px, pF, _fmax, _fl2):
+            callback(ctx.buf.view_for_callback(px, n, xin), ctx.buf.view_for_callback(pF, n, xin))
+
+        cb_c = _capi.CALLBACK(_cb)
+        ctx.check(ctx.lib.jfnk_set_callback(ctx.handle, cb_c, None))
+    try:
+        rc = ctx.lib.jfnk_newton(ctx.handle, ctx.buf.ptr(du), C.byref(opts), C.byref(hist.c))
+    finally:
+        if cb_c is not None:
+            ctx.lib.jfnk_set_callback(ctx.handle, _capi.CALLBACK(), None)
+    h = hist.as_dict()
+    F.last_history = h
+    if verbose:
+        for i in range(len(h["f_max"])):
+            sys.stdout.write(f"{i}:  |F(x)| = {h['f_max'][i]:g}; step {h['step'][i]:g}\n")
+        sys.stdout.flush()
+    x = ctx.buf.to_user(du, xin)
+    status = 1
+    if rc == _capi.NO_CONVERGENCE:
+        if raise_exception:
+            raise NoConvergence(x)
+        status = 2
+    else:
+        ctx.check(rc)
+    if full_output:
+        info = {"nit": h["nit"] + (1 if status == 1 else 0), "status": status, "success": status == 1,
+                "message": {1: "A solution was found at the specified tolerance.",
+                            2: "The maximum number of iterations allowed has been reached."}[status],
+                "history": h}
+        return x, info
+    return x

@@ -1,0 +1,304 @@
+"""Device residual handles: the objects passed as ``F`` to :func:`newton_krylov`.
+
+Each mirrors one of the reference's ``residual`` functions together with the module-level
+state it closes over (``Uo``, ``k``, ``g``, ``L`` ... / ``U.val``, ``dt``, ``CN_term``, ``Q.*``, ``J``):
+
+* :class:`SHResidual`        -- python_work/sh_scipy_nk.py:15-49 (and sh_vscode_nk.py, cpp main.cpp:19-32)
+* :class:`SHLinearised`      -- python_work/sh_linearised.py:16-57
+* :class:`PMA2Residual`      -- python_work/PMA2_nk.py:121-159 (+ Laplace_operator :263-343)
+* :class:`DropletResidual`   -- python_work/droplet.py:435-450 (+ Laplace_operator :601-681)
+
+``F(u)`` evaluates the residual on the GPU; ``F.jvp(v)`` is KrylovJacobian.matvec.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _capi
+from .context import Context, HistoryBuffer
+
+
+class _DeviceResidual:
+    """Common machinery: lazily (re)creates the engine context for the requested Krylov sizes."""
+
+    problem = None
+
+    def __init__(self, nx, ny, *, comm=None, inner_m=30, outer_k=10, gs="cgs2", gs_tau=2.0 ** -0.5,
+                 kernel_variant=0, buffers=None):
+        self.nx, self.ny = int(nx), int(ny)
+        self.comm = comm
+        self._krylov = (int(inner_m), int(outer_k))
+        self._gs = (gs, float(gs_tau))
+        self._variant = int(kernel_variant)
+        self._buffers = buffers
+        self._ctx = None
+        self.last_history = None
+
+    # slab owned by this rank
+    @property
+    def rows(self):
+        if self.comm is None:
+            return 0, self.ny
+        return self.comm.slab(self.ny)
+
+    @property
+    def n(self):
+        r0, nr = self.rows
+        return nr * self.nx
+
+    def context(self, inner_m=None, outer_k=None) -> Context:
+        want = (self._krylov[0] if inner_m is None else int(inner_m), self._krylov[1] if outer_k is None else int(outer_k))
+        if self._ctx is not None and want == self._krylov:
+            return self._ctx
+        if self._ctx is not None:
+            self._ctx.close()
+        self._krylov = want
+        r0, nr = self.rows
+        rank, nranks = (0, 1) if self.comm is None else (self.comm.rank, self.comm.size)
+        self._ctx = Context(self.problem, self.nx, self.ny, row0=r0, nrows=nr, rank=rank, nranks=nranks,
+                            inner_m=want[0], outer_k=want[1], gs=self._gs[0], gs_tau=self._gs[1],
+                            kernel_variant=self._variant, buffers=self._buffers)
+        if self.comm is not None and nranks > 1:
+            self.comm.attach(self._ctx)
+        self._configure(self._ctx)
+        return self._ctx
+
+    def _configure(self, ctx):  # push parameters / per-step state into a fresh context
+        raise NotImplementedError
+
+    # -- operator level ---------------------------------------------------------------------------
+    def __call__(self, u):
+        ctx = self.context()
+        du = ctx.vec(u, "u")
+        dF = ctx.buf.alloc(ctx.n)
+        ctx.check(ctx.lib.jfnk_residual(ctx.handle, ctx.buf.ptr(du), ctx.buf.ptr(dF)))
+        return ctx.buf.to_user(dF, u)
+
+    def linearize(self, x0, rdiff=None):
+        """Fix the Jacobian's linearisation point (KrylovJacobian.setup, _nonlin.py:1579-1598)."""
+        ctx = self.context()
+        dx = ctx.vec(x0, "x0")
+        ctx.check(ctx.lib.jfnk_linearize(ctx.handle, ctx.buf.ptr(dx), -1.0 if rdiff is None else float(rdiff)))
+        return self
+
+    def jvp(self, v):
+        """KrylovJacobian.matvec(v) at the linearisation point (_nonlin.py:1557-1565)."""
+        ctx = self.context()
+        dv = ctx.vec(v, "v")
+        out = ctx.buf.alloc(ctx.n)
+        ctx.check(ctx.lib.jfnk_jvp(ctx.handle, ctx.buf.ptr(dv), ctx.buf.ptr(out)))
+        return ctx.buf.to_user(out, v)
+
+    def lgmres(self, b, rtol=1e-5, maxiter=1, reset=True):
+        """scipy.sparse.linalg.lgmres(J, b, rtol=rtol, atol=0, maxiter=maxiter, inner_m, outer_k,
+        outer_v=<carried list>, prepend_outer_v=True, store_outer_Av=False) -> (x, info)."""
+        ctx = self.context()
+        if reset:
+            ctx.check(ctx.lib.jfnk_lgmres_reset(ctx.handle))
+        db = ctx.vec(b, "b")
+        dx = ctx.buf.alloc(ctx.n)
+        info, inner, res = C.c_int(0), C.c_int(0), C.c_double(0)
+        ctx.check(ctx.lib.jfnk_lgmres(ctx.handle, ctx.buf.ptr(db), ctx.buf.ptr(dx), float(rtol), int(maxiter),
+                                      C.byref(info), C.byref(res), C.byref(inner)))
+        self.last_lgmres = {"info": info.value, "res": res.value, "inner": inner.value}
+        return ctx.buf.to_user(dx, b), info.value
+
+
+class SHResidual(_DeviceResidual):
+    """Crank-Nicolson residual of Swift-Hohenberg on an N x N periodic grid (sh_scipy_nk.py:15-49).
+
+    ``h = d/N``; ``set_prev(Uo)`` plays the role of the script's ``Uo = U.copy(); UoUo = ...; UoUoUo = ...``.
+    """
+
+    problem = _capi.PROBLEM_SH
+
+    def __init__(self, N=64, d=40.0, k=0.2, r=0.01, g=1.0, *, h=None, **kw):
+        super().__init__(N, N, **kw)
+        self.N, self.d, self.k, self.r, self.g = int(N), float(d), float(k), float(r), float(g)
+        self.h = float(d) / N if h is None else float(h)
+        self._prev = None
+
+    def _configure(self, ctx):
+        ctx.check(ctx.lib.jfnk_sh_setup(ctx.handle, self.h, self.r, self.g, self.k))
+        if self._prev is not None:
+            ctx.check(ctx.lib.jfnk_set_prev(ctx.handle, ctx.buf.ptr(self._prev)))
+
+    def set_prev(self, Uo):
+        ctx = self.context()
+        self._prev = ctx.vec(Uo, "Uo")
+        ctx.check(ctx.lib.jfnk_set_prev(ctx.handle, ctx.buf.ptr(self._prev)))
+        return self
+
+    def spmv_lap(self, x):
+        """y = Lap @ x, the periodic 5-point Laplacian (sh_scipy_nk.py:34-35)."""
+        return self._spmv("jfnk_spmv_lap", x)
+
+    def spmv_L(self, x):
+        """y = L @ x, L = -Lap*Lap - 2 Lap + (r-1) I (sh_scipy_nk.py:39)."""
+        return self._spmv("jfnk_spmv_sh", x)
+
+    def _spmv(self, fn, x):
+        ctx = self.context()
+        dx = ctx.vec(x, "x")
+        dy = ctx.buf.alloc(ctx.n)
+        ctx.check(getattr(ctx.lib, fn)(ctx.handle, ctx.buf.ptr(dx), ctx.buf.ptr(dy)))
+        return ctx.buf.to_user(dy, x)
+
+    def steps(self, U, nsteps=1, history=None, **opts):
+        """``nsteps`` implicit time steps of the script's loop (sh_scipy_nk.py:53-61), entirely on the device:
+        ``Uo = U; U = newton_krylov(residual, Uo, **opts)``.  Returns the new field like ``U``."""
+        ctx = self.context()
+        du = ctx.vec(U, "U")
+        o = Context.make_opts(**opts)
+        hists = [HistoryBuffer() for _ in range(nsteps)]
+        arr = (_capi.History * nsteps)(*[h.c for h in hists])
+        rc = ctx.lib.jfnk_sh_step(ctx.handle, ctx.buf.ptr(du), int(nsteps), C.byref(o), arr)
+        for h, c in zip(hists, arr):
+            h.c = c
+        if history is not None:
+            history.extend(h.as_dict() for h in hists)
+        self._prev = None  # the engine's per-step constant now belongs to the last step
+        if rc != _capi.OK:
+            ctx.check(rc, ctx.buf.to_user(du, U))
+        return ctx.buf.to_user(du, U)
+
+
+class SHLinearised(_DeviceResidual):
+    """Linearly-implicit Swift-Hohenberg stepper (sh_linearised.py:16-57): per step solve
+    ``(I + D - L k/2) U+ = (I + L k/2) U`` with ``D = diag((5U - Uo)^2 k/16 - g k U)``.  The reference
+    factorises with SuperLU (``spsolve``); here the system is solved matrix-free by device LGMRES to ``rtol``."""
+
+    problem = _capi.PROBLEM_SH_LINEAR
+
+    def __init__(self, N=64, d=40.0, k=0.2, r=0.2, g=0.0, *, h=None, **kw):
+        super().__init__(N, N, **kw)
+        self.N, self.d, self.k, self.r, self.g = int(N), float(d), float(k), float(r), float(g)
+        self.h = float(d) / N if h is None else float(h)
+
+    def _configure(self, ctx):
+        ctx.check(ctx.lib.jfnk_sh_setup(ctx.handle, self.h, self.r, self.g, self.k))
+
+    def steps(self, U, Uo=None, nsteps=1, rtol=1e-13, maxiter=200):
+        """Advance ``nsteps``; returns ``(U_new, Uo_new)``.  ``Uo`` defaults to ``U`` (sh_linearised.py:28)."""
+        ctx = self.context()
+        dU = ctx.vec(U, "U")
+        dUo = ctx.vec(U if Uo is None else Uo, "Uo")
+        info, mv = C.c_int(0), C.c_int64(0)
+        ctx.check(ctx.lib.jfnk_shlin_step(ctx.handle, ctx.buf.ptr(dU), ctx.buf.ptr(dUo), int(nsteps), float(rtol),
+                                          int(maxiter), C.byref(info), C.byref(mv)))
+        self.last_info = {"info": info.value, "matvecs": mv.value}
+        return ctx.buf.to_user(dU, U), ctx.buf.to_user(dUo, U)
+
+    def prepare(self, U, Uo):
+        """Returns b = (I + L k/2) U and fixes D for :meth:`jvp` / :meth:`lgmres` (operator-level parity tests)."""
+        ctx = self.context()
+        dU, dUo = ctx.vec(U, "U"), ctx.vec(Uo, "Uo")
+        db = ctx.buf.alloc(ctx.n)
+        ctx.check(ctx.lib.jfnk_shlin_prepare(ctx.handle, ctx.buf.ptr(dU), ctx.buf.ptr(dUo), ctx.buf.ptr(db)))
+        return ctx.buf.to_user(db, U)
+
+
+class _MeshResidual(_DeviceResidual):
+    """Shared part of the moving-mesh problems: geometry and the mesh potential Q."""
+
+    def __init__(self, nx, ny, dksi, deta, bounds, **kw):
+        super().__init__(nx, ny, **kw)
+        self.dksi, self.deta = float(dksi), float(deta)
+        self.bounds = tuple(float(b) for b in bounds)  # (left, right, bottom, top)
+        self._Q = None
+        self._prev = None
+
+    def _configure_mesh(self, ctx):
+        ctx.check(ctx.lib.jfnk_mesh_setup(ctx.handle, self.dksi, self.deta, *self.bounds))
+        if self._Q is not None:
+            ctx.check(ctx.lib.jfnk_mesh_set_potential(ctx.handle, ctx.buf.ptr(self._Q)))
+
+    def set_mesh(self, Q):
+        """Mesh potential for this step: compute_Q_spatial_ders + J (+ the A_ij of Laplace_operator)."""
+        ctx = self.context()
+        self._Q = ctx.vec(Q, "Q")
+        ctx.check(ctx.lib.jfnk_mesh_set_potential(ctx.handle, ctx.buf.ptr(self._Q)))
+        return self
+
+    def laplace(self, v):
+        """(v_xx, v_yy) = Laplace_operator(v, D_ksi v, D_eta v)."""
+        ctx = self.context()
+        dv = ctx.vec(v, "v")
+        a, b = ctx.buf.alloc(ctx.n), ctx.buf.alloc(ctx.n)
+        ctx.check(ctx.lib.jfnk_mesh_laplace(ctx.handle, ctx.buf.ptr(dv), ctx.buf.ptr(a), ctx.buf.ptr(b)))
+        return ctx.buf.to_user(a, v), ctx.buf.to_user(b, v)
+
+
+class PMA2Residual(_MeshResidual):
+    """Residual of PMA2_nk.py:121-159 (p = 2) on an N x N computational grid over [-1, 1]^2.
+
+    The script's ``residual`` always uses the module-level ``dt = k`` (its time loop assigns a *local* ``dt``,
+    PMA2_nk.py:66,91), which is what ``dt`` means here.
+    """
+
+    problem = _capi.PROBLEM_PMA2
+
+    def __init__(self, N=51, *, lambd=1.0, beta=0.15, epsilon=0.0, m=3, dt=1e-4, endl=-1.0, endr=1.0, **kw):
+        dksi = (endr - endl) / (N - 1)
+        super().__init__(N, N, dksi, dksi, (endl, endr, endl, endr), **kw)
+        self.lambd, self.beta, self.epsilon, self.m, self.dt = float(lambd), float(beta), float(epsilon), int(m), float(dt)
+
+    def _configure(self, ctx):
+        self._configure_mesh(ctx)
+        ctx.check(ctx.lib.jfnk_pma2_setup(ctx.handle, self.lambd, self.beta, self.epsilon, self.m, self.dt))
+        if self._prev is not None:
+            ctx.check(ctx.lib.jfnk_pma2_set_prev(ctx.handle, ctx.buf.ptr(self._prev)))
+
+    def set_prev(self, Uval):
+        """``U.val = U.new.copy()`` and ``CN_term = compute_rhs_pde()`` (PMA2_nk.py:83,97)."""
+        ctx = self.context()
+        self._prev = ctx.vec(Uval, "U.val")
+        ctx.check(ctx.lib.jfnk_pma2_set_prev(ctx.handle, ctx.buf.ptr(self._prev)))
+        return self
+
+
+class DropletResidual(_MeshResidual):
+    """Residual of droplet.py:435-450 on the Nx x Ny moving mesh (defaults: droplet.py:23-53)."""
+
+    problem = _capi.PROBLEM_DROPLET
+
+    def __init__(self, Nx=91, Ny=61, *, endl=-3.0, endr=6.0, endb=-3.0, endt=3.0, epsilon=1e-2, n=6, m=3, Bo=0.01,
+                 alpha2=0.0, epsilon2=None, **kw):
+        dksi = (endr - endl) / (Nx - 1)
+        deta = (endt - endb) / (Ny - 1)
+        super().__init__(Nx, Ny, dksi, deta, (endl, endr, endb, endt), **kw)
+        self.epsilon, self.n_exp, self.m_exp, self.Bo, self.alpha2 = float(epsilon), int(n), int(m), float(Bo), float(alpha2)
+        self.epsilon2 = 1.0 / (endt - endb) if epsilon2 is None else float(epsilon2)
+        self._dt = None
+
+    def _configure(self, ctx):
+        self._configure_mesh(ctx)
+        ctx.check(ctx.lib.jfnk_droplet_setup(ctx.handle, self.epsilon, self.n_exp, self.m_exp, self.Bo, self.alpha2,
+                                             self.epsilon2))
+        if self._prev is not None:
+            ctx.check(ctx.lib.jfnk_droplet_set_prev(ctx.handle, ctx.buf.ptr(self._prev), self._dt))
+
+    def set_prev(self, Uval, dt):
+        """Per-step precompute of droplet.py:373-381: ``U.val``, ``P.val``, ``F = pde_rhs(...)`` and ``dt_n``."""
+        ctx = self.context()
+        self._prev = ctx.vec(Uval, "U.val")
+        self._dt = float(dt)
+        ctx.check(ctx.lib.jfnk_droplet_set_prev(ctx.handle, ctx.buf.ptr(self._prev), self._dt))
+        return self
+
+
+def load_droplet_state(path):
+    """Read an ``initdrop_*.txt`` state: one ``U.val[i] Q.val[i]`` pair per line (written by droplet.py:556-562).
+    The reference's own reader (droplet.py:564-576) hard-codes a Windows path separator."""
+    a = np.loadtxt(path)
+    return a[:, 0].copy(), a[:, 1].copy()
+
+
+def save_droplet_state(path, U, Q):
+    """Write a state in the reference's format (droplet.py:556-562)."""
+    with open(path, "w") as f:
+        for u, q in zip(np.asarray(U).ravel(), np.asarray(Q).ravel()):
+            f.write(str(float(u)) + " " + str(float(q)) + "\n")
