@@ -186,6 +186,17 @@ int jfnk_droplet_set_prev(jfnk_ctx* ctx, const double* dUval, double dt);
 /* ---- introspection for benches / tests --------------------------------------------------------- */
 /* number of kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t jfnk_launch_count(jfnk_ctx* ctx);
+/* per-kernel-class device timing (CUDA events on the launch stream) with the ALGORITHMIC bytes each launch
+ * moves; bench.py derives the roofline line from it.  jfnk_profile_read synchronises, fills up to `cap`
+ * classes, and clears the records. */
+typedef struct {
+  char name[32];
+  int64_t launches;
+  double ms;
+  double bytes;
+} jfnk_kernel_stat;
+int jfnk_profile_enable(jfnk_ctx* ctx, int on);
+int jfnk_profile_read(jfnk_ctx* ctx, jfnk_kernel_stat* out, int cap, int* count);
 /* BLAS-1 building blocks exposed for the roofline microbenchmarks and unit parity tests:
  * out[i] = V_i . w (i<nv), out[nv] = w.w ; V = nv vectors `stride` doubles apart starting at dV. */
 int jfnk_multi_dot(jfnk_ctx* ctx, int nv, const double* dV, size_t stride, const double* dw, double* out_host);

@@ -44,6 +44,10 @@ class History(C.Structure):
     ]
 
 
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("ms", C.c_double), ("bytes", C.c_double)]
+
+
 CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double)
 
 _P = C.c_void_p  # device pointers travel as plain addresses
@@ -81,6 +85,8 @@ SIGNATURES = {
     "jfnk_droplet_setup": (C.c_int, [_CTX, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
     "jfnk_droplet_set_prev": (C.c_int, [_CTX, _P, C.c_double]),
     "jfnk_launch_count": (C.c_int64, [_CTX]),
+    "jfnk_profile_enable": (C.c_int, [_CTX, C.c_int]),
+    "jfnk_profile_read": (C.c_int, [_CTX, C.POINTER(KernelStat), C.c_int, C.POINTER(C.c_int)]),
     "jfnk_multi_dot": (C.c_int, [_CTX, C.c_int, _P, C.c_size_t, _P, C.POINTER(C.c_double)]),
     "jfnk_multi_axpy": (C.c_int, [_CTX, C.c_int, _P, C.c_size_t, C.POINTER(C.c_double), _P, C.POINTER(C.c_double)]),
 }

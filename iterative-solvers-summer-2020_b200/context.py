@@ -95,7 +95,7 @@ class Context:
     """One ``jfnk_ctx``: a problem on a (slab of a) grid, with its Krylov workspace."""
 
     def __init__(self, problem, nx, ny, *, row0=0, nrows=None, rank=0, nranks=1, inner_m=30, outer_k=10,
-                 gs="cgs2", gs_tau=2.0 ** -0.5, kernel_variant=0, buffers=None):
+                 gs="cgs-ifneeded", gs_tau=0.25, kernel_variant=0, buffers=None):
         self.buf = buffers if buffers is not None else CudaBuffers()
         self.lib = self.buf.lib
         if gs not in _capi.GS_MODES:
@@ -151,6 +151,22 @@ class Context:
 
     def launches(self):
         return int(self.lib.jfnk_launch_count(self.handle))
+
+    # -- BLAS-1 building blocks of the Arnoldi process (exposed for micro-benchmarks and unit parity) ----
+    def multi_dot(self, dV, nv, stride, dw):
+        """host array [V_0.w, ..., V_{nv-1}.w, w.w] for nv device vectors `stride` doubles apart in dV."""
+        out = np.zeros(nv + 1)
+        self.check(self.lib.jfnk_multi_dot(self.handle, int(nv), self.buf.ptr(dV), C.c_size_t(int(stride)),
+                                           self.buf.ptr(dw), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def multi_axpy(self, dV, nv, stride, coef, dw):
+        """in place w -= sum_i coef[i] V_i ; returns ||w||^2."""
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        n2 = C.c_double(0.0)
+        self.check(self.lib.jfnk_multi_axpy(self.handle, int(nv), self.buf.ptr(dV), C.c_size_t(int(stride)),
+                                            coef.ctypes.data_as(C.POINTER(C.c_double)), self.buf.ptr(dw), C.byref(n2)))
+        return n2.value
 
     @staticmethod
     def make_opts(f_tol=None, f_rtol=None, x_tol=None, x_rtol=None, rdiff=None, maxiter=None, iter=None,

@@ -185,6 +185,20 @@ int jfnk_droplet_set_prev(jfnk_ctx* ctx, const double* dUval, double dt) {
   JF_TRY JF_CHECK_CTX(ctx); return done(ctx, ctx->eng->droplet_set_prev(dUval, dt)); JF_CATCH
 }
 
+int jfnk_profile_enable(jfnk_ctx* ctx, int on) {
+  JF_CHECK_CTX(ctx);
+  ctx->ops->profile_enable(on != 0);
+  return JFNK_OK;
+}
+int jfnk_profile_read(jfnk_ctx* ctx, jfnk_kernel_stat* out, int cap, int* count) {
+  JF_TRY JF_CHECK_CTX(ctx);
+  static_assert(sizeof(jfnk_kernel_stat) == sizeof(KernelStat), "jfnk_kernel_stat layout");
+  int k = ctx->ops->profile_read(reinterpret_cast<KernelStat*>(out), cap);
+  if (count) *count = k;
+  return done(ctx, ctx->ops->status());
+  JF_CATCH
+}
+
 int64_t jfnk_launch_count(jfnk_ctx* ctx) { return (ctx && ctx->ops) ? ctx->ops->launches() : 0; }
 
 int jfnk_multi_dot(jfnk_ctx* ctx, int nv, const double* dV, size_t stride, const double* dw, double* out_host) {

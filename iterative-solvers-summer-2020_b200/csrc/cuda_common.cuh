@@ -1,0 +1,132 @@
+// Common device helpers: streaming 128-bit loads, warp/block reductions and the deterministic
+// "last block finalises" cross-block reduction used by every norm / dot kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "device_ops.h"
+
+namespace jfnk {
+
+constexpr int kMaxBlocks = 148 * 8; // persistent-style grids: a multiple of the B200's 148 SMs
+constexpr int kPartialStride = JF_MAXV + 4;
+
+struct PtrList {
+  const double* p[JF_MAXV];
+};
+
+struct ReduceWs {
+  double* partials;   // [kMaxBlocks * kPartialStride]
+  unsigned* ticket;   // zero between launches
+};
+
+// read-only streaming loads (data is touched once per kernel; keep it out of L1)
+__device__ __forceinline__ double2 ldg2(const double* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double ldg1(const double* p) { return __ldg(p); }
+__device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-reduce K per-thread values (op: 0 sum, 1 max per entry, given by the bit mask `maxmask`), write this
+// block's partials, and let the LAST block to arrive reduce all partials in a fixed order and store the K
+// results to out[0..K).  Deterministic for a fixed grid.  Must be called by all threads of all blocks.
+template <int K>
+__device__ __forceinline__ void grid_reduce(double (&val)[K], unsigned maxmask, const ReduceWs& ws, double* out) {
+  __shared__ double sm[32][K];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double v = ((maxmask >> k) & 1u) ? warp_max(val[k]) : warp_sum(val[k]);
+    if (lane == 0) sm[warp][k] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      bool mx = (maxmask >> k) & 1u;
+      double v = (lane < nwarp) ? sm[lane][k] : 0.0; // max entries are non-negative (abs values)
+      v = mx ? warp_max(v) : warp_sum(v);
+      if (lane == 0) ws.partials[(size_t)blockIdx.x * kPartialStride + k] = v;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(ws.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int k = warp; k < K; k += nwarp) {
+      bool mx = (maxmask >> k) & 1u;
+      double v = 0.0;
+      for (unsigned b = lane; b < gridDim.x; b += 32) {
+        double pv = __ldcg(&ws.partials[(size_t)b * kPartialStride + k]);
+        v = mx ? fmax(v, pv) : v + pv;
+      }
+      v = mx ? warp_max(v) : warp_sum(v);
+      if (lane == 0) out[k] = v;
+    }
+    if (threadIdx.x == 0) *ws.ticket = 0u;
+  }
+}
+
+// multi-dot variant: val[0..nv) are dot accumulators (nv <= KMAX-1 at run time), val[KMAX-1] is w.w.
+// Writes out[0..nv) = dots, out[nv] = w.w.  All array indices are compile-time so val[] stays in registers.
+template <int KMAX>
+__device__ __forceinline__ void grid_reduce_sums(double (&val)[KMAX], int nv, const ReduceWs& ws, double* out) {
+  __shared__ double sm[8][KMAX];
+  __shared__ bool is_last;
+  const int K = nv + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5; // nwarp <= 8
+#pragma unroll
+  for (int k = 0; k < KMAX - 1; ++k) {
+    if (k < nv) {
+      double v = warp_sum(val[k]);
+      if (lane == 0) sm[warp][k] = v;
+    }
+  }
+  {
+    double v = warp_sum(val[KMAX - 1]);
+    if (lane == 0) sm[warp][nv] = v;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double v = 0.0;
+    for (int w = 0; w < nwarp; ++w) v += sm[w][k];
+    ws.partials[(size_t)blockIdx.x * kPartialStride + k] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(ws.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int k = warp; k < K; k += nwarp) {
+      double v = 0.0;
+      for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(&ws.partials[(size_t)b * kPartialStride + k]);
+      v = warp_sum(v);
+      if (lane == 0) out[k] = v;
+    }
+    if (threadIdx.x == 0) *ws.ticket = 0u;
+  }
+}
+
+} // namespace jfnk

@@ -1,0 +1,486 @@
+// CudaOps: the device backend of libjfnk.so -- launchers of the sm_100a kernels, the device scalar arena,
+// and the NCCL plumbing of the slab decomposition (halo send/recv + allreduce of Krylov scalars).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "backend.h"
+#include "blas_kernels.cuh"
+#include "mesh_kernels.cuh"
+#include "nccl_dl.h"
+#include "sh_kernels.cuh"
+
+namespace jfnk {
+
+namespace {
+
+inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+// kernel classes of the per-kernel timing (bench.py roofline); bytes are the ALGORITHMIC bytes of DESIGN.md
+enum KClass { K_MDOT = 0, K_GS_UPDATE, K_MAXPY, K_LINCOMB, K_SPMV_LAP, K_SPMV_L, K_SET_PREV, K_RESIDUAL, K_JVP,
+              K_SHLIN, K_MESH, K_SCALAR, K_MDOT2, K_GS_UPDATE2, K_COUNT };
+const char* const kClassName[K_COUNT] = {"mdot", "gs_update", "maxpy", "lincomb", "spmv_lap", "spmv_L", "set_prev",
+                                         "sh_residual", "sh_jvp", "shlin", "mesh", "scalar", "mdot_pass2",
+                                         "gs_update_pass2"};
+
+class CudaOps : public DeviceOps {
+ public:
+  CudaOps(const jfnk_config& c, std::string& why, bool& ok) : variant_(c.kernel_variant) {
+    g_.nx = c.nx; g_.ny = c.ny; g_.row0 = c.row0; g_.nrows = c.nrows; g_.rank = c.rank; g_.nranks = c.nranks;
+    stream_ = (cudaStream_t)c.stream;
+    ok = false;
+    if (!ck(cudaGetDevice(&device_), "cudaGetDevice")) { why = err_; return; }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_);
+    sms_ = sms > 0 ? sms : 148;
+    if (!ck(cudaMalloc(&S_, sizeof(double) * JS_COUNT), "cudaMalloc(scalars)")) { why = err_; return; }
+    if (!ck(cudaMemsetAsync(S_, 0, sizeof(double) * JS_COUNT, stream_), "cudaMemset(scalars)")) { why = err_; return; }
+    if (!ck(cudaMalloc(&ws_.partials, sizeof(double) * (size_t)kMaxBlocks * kPartialStride), "cudaMalloc(partials)")) { why = err_; return; }
+    if (!ck(cudaMalloc(&ws_.ticket, sizeof(unsigned)), "cudaMalloc(ticket)")) { why = err_; return; }
+    if (!ck(cudaMemsetAsync(ws_.ticket, 0, sizeof(unsigned), stream_), "cudaMemset(ticket)")) { why = err_; return; }
+    if (!ck(cudaMallocHost(&pinned_, sizeof(double) * JS_COUNT), "cudaMallocHost")) { why = err_; return; }
+    if (g_.nranks > 1) {
+      // row halos of the linearisation point (x0), of the operand vector (z / dx) and of a generic field
+      size_t hb = sizeof(double) * 2 * (size_t)g_.nx;
+      for (int i = 0; i < 6; ++i)
+        if (!ck(cudaMalloc(&halo_[i], hb), "cudaMalloc(halo)")) { why = err_; return; }
+    }
+    ok = true;
+  }
+  ~CudaOps() override {
+    if (comm_ && nccl_) nccl_->CommDestroy(comm_);
+    for (auto& r : recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : free_events_) cudaEventDestroy(e);
+    for (int i = 0; i < 6; ++i) if (halo_[i]) cudaFree(halo_[i]);
+    if (pinned_) cudaFreeHost(pinned_);
+    if (ws_.ticket) cudaFree(ws_.ticket);
+    if (ws_.partials) cudaFree(ws_.partials);
+    if (S_) cudaFree(S_);
+  }
+
+  int64_t launches() const override { return launches_; }
+  void profile_enable(bool on) override { profiling_ = on; }
+  int profile_read(KernelStat* out, int cap) override {
+    cudaStreamSynchronize(stream_);
+    double ms[K_COUNT] = {0}, by[K_COUNT] = {0};
+    int64_t cnt[K_COUNT] = {0};
+    for (auto& r : recs_) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cls] += t; by[r.cls] += r.bytes; cnt[r.cls]++; }
+      free_events_.push_back(r.a);
+      free_events_.push_back(r.b);
+    }
+    recs_.clear();
+    int k = 0;
+    for (int c = 0; c < K_COUNT && k < cap; ++c) {
+      if (!cnt[c]) continue;
+      memset(&out[k], 0, sizeof(KernelStat));
+      strncpy(out[k].name, kClassName[c], sizeof(out[k].name) - 1);
+      out[k].launches = cnt[c]; out[k].ms = ms[c]; out[k].bytes = by[c];
+      ++k;
+    }
+    return k;
+  }
+  struct ProfRec { int cls; double bytes; cudaEvent_t a, b; };
+  cudaEvent_t get_event() {
+    cudaEvent_t e;
+    if (!free_events_.empty()) { e = free_events_.back(); free_events_.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+  }
+  // scoped timer around one launch: records events on the launch stream when profiling is enabled
+  struct Prof {
+    CudaOps* o; bool on;
+    Prof(CudaOps* ops, int cls, double bytes) : o(ops), on(ops->profiling_) {
+      o->launches_++;
+      if (!on) return;
+      ProfRec r; r.cls = cls; r.bytes = bytes; r.a = o->get_event(); r.b = o->get_event();
+      cudaEventRecord(r.a, o->stream_);
+      o->recs_.push_back(r);
+    }
+    ~Prof() { if (on) cudaEventRecord(o->recs_.back().b, o->stream_); }
+  };
+  double nb(double vectors) const { return vectors * 8.0 * (double)g_.n(); }
+  int status() override {
+    if (code_ == JFNK_OK) {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) { code_ = JFNK_CUDA_ERROR; err_ = std::string("CUDA error: ") + cudaGetErrorString(e); }
+    }
+    return code_;
+  }
+  const char* last_error() const override { return err_.c_str(); }
+
+  // ---- scalars ----------------------------------------------------------------------------------
+  void read_scalars(int off, int cnt, double* host) override {
+    if (!ck(cudaMemcpyAsync(pinned_, S_ + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, stream_), "D2H scalars")) return;
+    if (!ck(cudaStreamSynchronize(stream_), "cudaStreamSynchronize")) return;
+    memcpy(host, pinned_, sizeof(double) * cnt);
+  }
+  void write_scalars(int off, int cnt, const double* host) override {
+    ck(cudaMemcpyAsync(S_ + off, host, sizeof(double) * cnt, cudaMemcpyHostToDevice, stream_), "H2D scalars");
+  }
+  void allreduce_sum(int off, int cnt) override {
+    if (g_.nranks > 1) nck(nccl_->AllReduce(S_ + off, S_ + off, cnt, ncclDouble, ncclSum, comm_, stream_), "ncclAllReduce(sum)");
+  }
+  void allreduce_max(int off, int cnt) override {
+    if (g_.nranks > 1) nck(nccl_->AllReduce(S_ + off, S_ + off, cnt, ncclDouble, ncclMax, comm_, stream_), "ncclAllReduce(max)");
+  }
+
+  // ---- BLAS-1 -------------------------------------------------------------------------------------
+  int stream_grid(size_t items, int per_block) const {
+    size_t b = (items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    size_t cap = (size_t)sms_ * 8;
+    if (cap > (size_t)kMaxBlocks) cap = kMaxBlocks;
+    return (int)std::min(b, cap);
+  }
+
+  template <int NV>
+  void mdot_launch(bool vec, const PtrList& L, int nv, const double* w, int out_off, int guard, double tau2) {
+    size_t n = g_.n();
+    // register-heavy instantiations run fewer, fatter blocks: one or two 256-thread CTAs per SM
+    int blocks = std::min(stream_grid(vec ? n / 2 : n, 256), sms_ * (NV <= 8 ? 8 : (NV <= 16 ? 4 : 2)));
+    Prof prof(this, guard ? K_MDOT2 : K_MDOT, nb(nv + 1)); // pass-2 launches may early-exit on device
+    if (vec) mdot_kernel<NV><<<blocks, 256, 0, stream_>>>(L, nv, w, n, S_, out_off, guard, tau2, ws_);
+    else mdot_scalar_kernel<NV><<<blocks, 256, 0, stream_>>>(L, nv, w, n, S_, out_off, guard, tau2, ws_);
+  }
+  void mdot(int nv, const double* const* V, const double* w, int out_off, int guard, double tau2) override {
+    PtrList L;
+    bool vec = aligned16(w);
+    for (int i = 0; i < nv; ++i) { L.p[i] = V[i]; vec = vec && aligned16(V[i]); }
+    for (int i = nv; i < JF_MAXV; ++i) L.p[i] = nullptr;
+    if (nv <= 2) mdot_launch<2>(vec, L, nv, w, out_off, guard, tau2);
+    else if (nv <= 4) mdot_launch<4>(vec, L, nv, w, out_off, guard, tau2);
+    else if (nv <= 8) mdot_launch<8>(vec, L, nv, w, out_off, guard, tau2);
+    else if (nv <= 12) mdot_launch<12>(vec, L, nv, w, out_off, guard, tau2);
+    else if (nv <= 16) mdot_launch<16>(vec, L, nv, w, out_off, guard, tau2);
+    else if (nv <= 20) mdot_launch<20>(vec, L, nv, w, out_off, guard, tau2);
+    else if (nv <= 24) mdot_launch<24>(vec, L, nv, w, out_off, guard, tau2);
+    else if (nv <= 28) mdot_launch<28>(vec, L, nv, w, out_off, guard, tau2);
+    else if (nv <= 32) mdot_launch<32>(vec, L, nv, w, out_off, guard, tau2);
+    else if (nv <= 40) mdot_launch<40>(vec, L, nv, w, out_off, guard, tau2);
+    else mdot_launch<JF_MAXV>(vec, L, nv, w, out_off, guard, tau2);
+  }
+
+  template <int MODE>
+  void maxpy_launch(int nv, const double* const* V, double* w, int c_off, int n2_off, int guard, double tau2) {
+    PtrList L;
+    bool vec = aligned16(w);
+    for (int i = 0; i < nv; ++i) { L.p[i] = V[i]; vec = vec && aligned16(V[i]); }
+    for (int i = nv; i < JF_MAXV; ++i) L.p[i] = nullptr;
+    size_t n = g_.n();
+    int blocks = stream_grid(vec ? n / 2 : n, 256);
+    Prof prof(this, MODE == 2 ? K_MAXPY : (guard ? K_GS_UPDATE2 : K_GS_UPDATE), nb(MODE == 2 ? nv + 1 : nv + 2));
+    if (vec) maxpy_kernel<MODE, true><<<blocks, 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, guard, tau2, ws_);
+    else maxpy_kernel<MODE, false><<<blocks, 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, guard, tau2, ws_);
+  }
+  void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int guard, double tau2) override {
+    maxpy_launch<0>(nv, V, w, rd_off, n2_off, guard, tau2);
+  }
+  void maxpy_sub(int nv, const double* const* V, double* w, int n2_off) override {
+    maxpy_launch<1>(nv, V, w, JS_COEF, n2_off, 0, 0.0);
+  }
+  void maxpy(int nz, const double* const* Z, double* out, int n2_off) override {
+    maxpy_launch<2>(nz, Z, out, JS_COEF, n2_off, 0, 0.0);
+  }
+  void lincomb(double* out, ScalarRef a, const double* x, ScalarRef b, const double* y, int n2_off) override {
+    size_t n = g_.n();
+    bool vec = aligned16(out) && aligned16(x) && (!y || aligned16(y));
+    int blocks = stream_grid(vec ? n / 2 : n, 256);
+    Prof prof(this, K_LINCOMB, nb(y ? 3 : 2));
+    if (vec) lincomb_kernel<true><<<blocks, 256, 0, stream_>>>(out, a, x, b, y, n, S_, n2_off, ws_);
+    else lincomb_kernel<false><<<blocks, 256, 0, stream_>>>(out, a, x, b, y, n, S_, n2_off, ws_);
+  }
+  void diff_scale(double* out, const double* x, const double* y, ScalarRef div) override {
+    size_t n = g_.n();
+    Prof prof(this, K_LINCOMB, nb(3));
+    diff_scale_kernel<<<stream_grid(n, 256), 256, 0, stream_>>>(out, x, y, div, n, S_);
+  }
+  void copy(double* dst, const double* src) override {
+    if (dst == src) return;
+    ck(cudaMemcpyAsync(dst, src, sizeof(double) * g_.n(), cudaMemcpyDeviceToDevice, stream_), "D2D copy");
+  }
+  void maxabs(const double* v, int out_off) override {
+    size_t n = g_.n();
+    Prof prof(this, K_LINCOMB, nb(1));
+    maxabs_kernel<<<stream_grid(n, 256), 256, 0, stream_>>>(v, n, S_, out_off, ws_);
+  }
+  void givens(int j, int pass2, double tau2) override {
+    Prof prof(this, K_SCALAR, 0.0);
+    givens_kernel<<<1, 1, 0, stream_>>>(S_, j, pass2, tau2);
+  }
+  void lsq(int nit, const int* zn2_idx, int scale_n2_idx) override {
+    IdxList L;
+    for (int i = 0; i < JF_MAXV; ++i) L.v[i] = i < nit ? zn2_idx[i] : 0;
+    Prof prof(this, K_SCALAR, 0.0);
+    lsq_kernel<<<1, 1, 0, stream_>>>(S_, nit, L, scale_n2_idx);
+  }
+
+  // ---- Swift-Hohenberg ------------------------------------------------------------------------------
+  void sh_setup(const SHParams& p) override { shp_ = p; }
+
+  // 2-row halos of a slab-local field.  One rank: periodic wrap inside the field itself.
+  // slot 0: linearisation point, 1: operand (z, dx), 2: generic
+  void halo_ptrs(const double* v, int slot, bool exchange, const double*& top, const double*& bot) {
+    if (g_.nranks == 1) {
+      top = v + (size_t)(g_.nrows - 2) * g_.nx;
+      bot = v;
+      return;
+    }
+    double* t = halo_[2 * slot];
+    double* b = halo_[2 * slot + 1];
+    if (exchange) {
+      size_t cnt = 2 * (size_t)g_.nx;
+      int prev = (g_.rank + g_.nranks - 1) % g_.nranks, next = (g_.rank + 1) % g_.nranks;
+      // message A: my first two rows -> previous rank's bottom halo ; message B: my last two rows -> next rank's top halo.
+      // The order (send A, send B, recv A, recv B) keeps the pairing right when prev == next (two ranks).
+      nck(nccl_->GroupStart(), "ncclGroupStart");
+      nck(nccl_->Send(v, cnt, ncclDouble, prev, comm_, stream_), "ncclSend");
+      nck(nccl_->Send(v + (size_t)(g_.nrows - 2) * g_.nx, cnt, ncclDouble, next, comm_, stream_), "ncclSend");
+      nck(nccl_->Recv(b, cnt, ncclDouble, next, comm_, stream_), "ncclRecv");
+      nck(nccl_->Recv(t, cnt, ncclDouble, prev, comm_, stream_), "ncclRecv");
+      nck(nccl_->GroupEnd(), "ncclGroupEnd");
+    }
+    top = t; bot = b;
+  }
+
+  bool use_march(const ShArgs& A) const {
+    if (variant_ == 1) return false;
+    bool ok = (g_.nx % 2 == 0) && aligned16(A.x) && aligned16(A.xtop) && aligned16(A.xbot) && aligned16(A.out) &&
+              (!A.v || (aligned16(A.v) && aligned16(A.vtop) && aligned16(A.vbot))) && (!A.d || aligned16(A.d)) &&
+              (!A.f0 || aligned16(A.f0)) && (!A.out2 || aligned16(A.out2));
+    if (!ok) return false;
+    if (variant_ == 2) return true;
+    return g_.nx >= 128 && g_.nrows >= 32; // small grids are launch-latency bound: one thread per point
+  }
+
+  template <int OP, bool HAS_V>
+  void sh_launch(ShArgs& A) {
+    A.nx = g_.nx; A.nrows = g_.nrows;
+    // algorithmic traffic in vectors of 8 B/point: inputs read once + outputs written once
+    const int cls = OP == OP_LAP ? K_SPMV_LAP : OP == OP_L ? K_SPMV_L : OP == OP_SETPREV ? K_SET_PREV
+                  : OP == OP_RESID ? K_RESIDUAL : OP == OP_JVP ? K_JVP : K_SHLIN;
+    const double vecs = OP == OP_LAP || OP == OP_L || OP == OP_SETPREV ? 2.0
+                      : OP == OP_RESID ? (3.0 + (HAS_V ? 1.0 : 0.0) + (A.out2 ? 1.0 : 0.0))
+                      : OP == OP_JVP ? 5.0 : OP == OP_LINPREP ? 4.0 : 3.0;
+    Prof prof(this, cls, nb(vecs));
+    if (use_march(A)) {
+      int strips = (g_.nx + 63) / 64;
+      long long target = (long long)sms_ * 16; // warps wanted in flight
+      long long ry = ((long long)g_.nrows * strips) / target;
+      if (ry < 8) ry = 8;
+      if (ry > 64) ry = 64;
+      if (ry > g_.nrows) ry = g_.nrows;
+      A.ry = (int)ry;
+      long long chunks = (g_.nrows + ry - 1) / ry;
+      long long warps = chunks * strips;
+      int blocks = (int)((warps + kMarchWarps - 1) / kMarchWarps);
+      sh_march_kernel<OP, HAS_V><<<blocks, kMarchWarps * 32, 0, stream_>>>(A, shp_, S_, ws_);
+    } else {
+      A.ry = 0;
+      int blocks = stream_grid(g_.n(), 256);
+      sh_point_kernel<OP, HAS_V><<<blocks, 256, 0, stream_>>>(A, shp_, S_, ws_);
+    }
+  }
+
+  ShArgs blank() {
+    ShArgs A;
+    memset(&A, 0, sizeof(A));
+    A.a = sref(0.0); A.div = sref(1.0);
+    return A;
+  }
+
+  void sh_spmv(int which, const double* x, double* y) override {
+    ShArgs A = blank();
+    A.x = x; halo_ptrs(x, 2, true, A.xtop, A.xbot);
+    A.out = y;
+    if (which) sh_launch<OP_L, false>(A); else sh_launch<OP_LAP, false>(A);
+  }
+  void sh_set_prev(const double* uo, double* d) override {
+    ShArgs A = blank();
+    A.x = uo; halo_ptrs(uo, 2, true, A.xtop, A.xbot);
+    A.out = d;
+    sh_launch<OP_SETPREV, false>(A);
+  }
+  void sh_residual(const double* x, const double* v, ScalarRef a, const double* d, double* xt_out, double* F,
+                   int norm_off) override {
+    ShArgs A = blank();
+    A.x = x; halo_ptrs(x, 2, true, A.xtop, A.xbot);
+    A.d = d; A.out = F; A.out2 = xt_out; A.norm_off = norm_off;
+    if (v) {
+      A.v = v; halo_ptrs(v, 1, true, A.vtop, A.vbot);
+      A.a = a;
+      sh_launch<OP_RESID, true>(A);
+    } else {
+      sh_launch<OP_RESID, false>(A);
+    }
+  }
+  void sh_bind_x0(const double* x0) override {
+    const double *t, *b;
+    halo_ptrs(x0, 0, true, t, b);
+  }
+  void sh_jvp(const double* x0, const double* z, ScalarRef sc, ScalarRef div, const double* d, const double* f0,
+              double* w) override {
+    ShArgs A = blank();
+    A.x = x0; halo_ptrs(x0, 0, false, A.xtop, A.xbot);
+    A.v = z; halo_ptrs(z, 1, true, A.vtop, A.vbot);
+    A.a = sc; A.div = div; A.d = d; A.f0 = f0; A.out = w;
+    sh_launch<OP_JVP, true>(A);
+  }
+  void shlin_prepare(const double* U, const double* Uo, double* D, double* b) override {
+    ShArgs A = blank();
+    A.x = U; halo_ptrs(U, 2, true, A.xtop, A.xbot);
+    A.f0 = Uo; A.out = b; A.out2 = D;
+    sh_launch<OP_LINPREP, false>(A);
+  }
+  void shlin_matvec(const double* z, ScalarRef a, const double* D, double* w) override {
+    ShArgs A = blank();
+    A.x = z; halo_ptrs(z, 1, true, A.xtop, A.xbot);
+    A.div = a; A.d = D; A.out = w;
+    sh_launch<OP_LINMV, false>(A);
+  }
+
+  // ---- moving mesh -------------------------------------------------------------------------------------
+  static MetricCPtrs cptrs(const double* const* M) {
+    MetricCPtrs P;
+    for (int i = 0; i < 7; ++i) P.m[i] = M[i];
+    return P;
+  }
+  void mesh_metrics(const MeshParams& mp, const double* Q, double* const* M) override {
+    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MetricPtrs P;
+    for (int i = 0; i < 7; ++i) P.m[i] = M[i];
+    Prof prof(this, K_MESH, nb(8));
+    mesh_metrics_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, Q, P);
+  }
+  void mesh_laplace(const MeshParams& mp, const double* const* M, const double* v, double* vxx, double* vyy,
+                    int sum_only, int deriv_bc) override {
+    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    Prof prof(this, K_MESH, nb(sum_only ? 6 : 7));
+    mesh_laplace_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, cptrs(M), v, vxx, vyy, sum_only, deriv_bc);
+  }
+  void pma2_rhs(const Pma2Params& pp, const double* u, const double* lap2, double* out) override {
+    MeshParams mp; memset(&mp, 0, sizeof(mp)); mp.dksi = mp.deta = 1.0;
+    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    Prof prof(this, K_MESH, nb(3));
+    pma2_rhs_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, pp, u, lap2, out);
+  }
+  void pma2_combine(const Pma2Params& pp, const double* u, const double* uval, const double* rhs, const double* cn,
+                    double* F, int norm_off) override {
+    Prof prof(this, K_MESH, nb(5));
+    pma2_combine_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(g_.n(), pp, u, uval, rhs, cn, F, S_, norm_off, ws_);
+  }
+  void droplet_pressure(const DropletParams& dp, const double* h, const double* lap, double* p) override {
+    Prof prof(this, K_MESH, nb(3));
+    droplet_pressure_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(g_.n(), dp, h, lap, p);
+  }
+  void droplet_flux(const MeshParams& mp, const DropletParams& dp, const double* const* M, const double* p,
+                    const double* h, double* A, double* B) override {
+    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    Prof prof(this, K_MESH, nb(8));
+    droplet_flux_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, dp, cptrs(M), p, h, A, B);
+  }
+  void droplet_div(const MeshParams& mp, const double* const* M, const double* A, const double* B, double* out) override {
+    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    Prof prof(this, K_MESH, nb(7));
+    droplet_div_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, cptrs(M), A, B, out);
+  }
+  void droplet_combine(const DropletParams& dp, const double* u, const double* uval, const double* F2,
+                       const double* Fprev, double* F, int norm_off) override {
+    Prof prof(this, K_MESH, nb(5));
+    droplet_combine_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(g_.n(), dp, u, uval, F2, Fprev, F, S_, norm_off, ws_);
+  }
+
+  // ---- NCCL ----------------------------------------------------------------------------------------------
+  int comm_init(const void* id128, std::string& why) {
+    if (g_.nranks == 1) return JFNK_OK;
+    nccl_ = nccl_api(why);
+    if (!nccl_) return JFNK_NCCL_ERROR;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclResult_t r = nccl_->CommInitRank(&comm_, g_.nranks, id, g_.rank);
+    if (r != ncclSuccess) { why = std::string("ncclCommInitRank: ") + nccl_->GetErrorString(r); comm_ = nullptr; return JFNK_NCCL_ERROR; }
+    return JFNK_OK;
+  }
+
+ private:
+  bool ck(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    if (code_ == JFNK_OK) { code_ = JFNK_CUDA_ERROR; err_ = std::string(what) + ": " + cudaGetErrorString(e); }
+    return false;
+  }
+  void nck(ncclResult_t r, const char* what) {
+    if (r == ncclSuccess) return;
+    if (code_ == JFNK_OK) { code_ = JFNK_NCCL_ERROR; err_ = std::string(what) + ": " + (nccl_ ? nccl_->GetErrorString(r) : "nccl"); }
+  }
+
+  Grid g_;
+  int variant_;
+  int device_ = 0, sms_ = 148;
+  cudaStream_t stream_ = nullptr;
+  double* S_ = nullptr;
+  double* pinned_ = nullptr;
+  ReduceWs ws_ = {nullptr, nullptr};
+  double* halo_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  SHParams shp_;
+  int64_t launches_ = 0;
+  bool profiling_ = false;
+  std::vector<ProfRec> recs_;
+  std::vector<cudaEvent_t> free_events_;
+  int code_ = JFNK_OK;
+  std::string err_;
+  const NcclApi* nccl_ = nullptr;
+  ncclComm_t comm_ = nullptr;
+};
+
+__global__ void probe_kernel(int* out) { *out = 100; }
+
+} // namespace
+
+int backend_device_ok(std::string& why) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    why = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    cudaGetLastError();
+    return 0;
+  }
+  // the library carries sm_100a SASS only: make sure a kernel image actually loads on this device
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, probe_kernel);
+  if (e != cudaSuccess) {
+    why = std::string("sm_100a kernel image does not load on this device: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return 0;
+  }
+  return 1;
+}
+
+DeviceOps* backend_make_ops(const jfnk_config& cfg, std::string& why, int& code) {
+  code = JFNK_CUDA_ERROR;
+  if (!backend_device_ok(why)) return nullptr;
+  bool ok = false;
+  CudaOps* ops = new CudaOps(cfg, why, ok);
+  if (!ok) { delete ops; return nullptr; }
+  return ops;
+}
+
+int backend_unique_id(void* id128, std::string& why) {
+  const NcclApi* api = nccl_api(why);
+  if (!api) return JFNK_NCCL_ERROR;
+  ncclUniqueId id;
+  ncclResult_t r = api->GetUniqueId(&id);
+  if (r != ncclSuccess) { why = std::string("ncclGetUniqueId: ") + api->GetErrorString(r); return JFNK_NCCL_ERROR; }
+  memcpy(id128, &id, sizeof(id));
+  return JFNK_OK;
+}
+
+int backend_comm_init(DeviceOps* ops, const void* id128, std::string& why) {
+  return static_cast<CudaOps*>(ops)->comm_init(id128, why);
+}
+
+} // namespace jfnk

@@ -46,10 +46,21 @@ struct MeshParams {
 struct Pma2Params { double lambd, beta, epsilon; int m; double dt; };
 struct DropletParams { double epsilon; int n_exp, m_exp; double Bo, alpha2, epsilon2; double dt; };
 
+// per-kernel-class timing (CUDA events on the launch stream) for bench.py's roofline line
+struct KernelStat {
+  char name[32];
+  int64_t launches;
+  double ms;    // summed device time of the launches
+  double bytes; // summed ALGORITHMIC bytes of the launches (per-kernel table)
+};
+
 class DeviceOps {
  public:
   virtual ~DeviceOps() {}
   virtual int64_t launches() const = 0;
+  virtual void profile_enable(bool on) = 0;
+  // synchronises, aggregates and clears the records; returns the number of classes written (<= cap)
+  virtual int profile_read(KernelStat* out, int cap) = 0;
   // 0 when no asynchronous device error is pending, else JFNK_CUDA_ERROR / JFNK_NCCL_ERROR (message via last_error()).
   virtual int status() = 0;
   virtual const char* last_error() const = 0;

@@ -22,6 +22,7 @@ struct SHParams {
   double c0, c1, c2, c3; // 13-point coefficients of L
   double e;              // 1/h^2 (5-point Laplacian)
   double g, k, r;        // PDE parameters, time step
+  double inv_k;          // 1/k
 };
 
 JF_HD SHParams make_sh_params(double h, double r, double g, double k) {
@@ -32,7 +33,7 @@ JF_HD SHParams make_sh_params(double h, double r, double g, double k) {
   p.c1 = 8.0 * e * e - 2.0 * e;
   p.c2 = -2.0 * e * e;
   p.c3 = -e * e;
-  p.g = g; p.k = k; p.r = r;
+  p.g = g; p.k = k; p.r = r; p.inv_k = 1.0 / k;
   return p;
 }
 
@@ -50,8 +51,9 @@ JF_HD double sh_nonlin(const SHParams& p, double u, double Lu) {
 }
 // G(u) = u/k - N(u)/2 ;  F(u) = G(u) - d  with  d = Uo/k + N(Uo)/2   (sh_scipy_nk.py:49 regrouped so the
 // previous-time-level terms are one per-step constant field d).
-JF_HD double sh_G(const SHParams& p, double u, double Lu) { return u / p.k - sh_nonlin(p, u, Lu) / 2.0; }
-JF_HD double sh_prev_const(const SHParams& p, double uo, double Luo) { return uo / p.k + sh_nonlin(p, uo, Luo) / 2.0; }
+// (1/k is applied as a multiplication by inv_k: one rounding like the division, no fp64 divide in the hot loop.)
+JF_HD double sh_G(const SHParams& p, double u, double Lu) { return u * p.inv_k - sh_nonlin(p, u, Lu) * 0.5; }
+JF_HD double sh_prev_const(const SHParams& p, double uo, double Luo) { return uo * p.inv_k + sh_nonlin(p, uo, Luo) * 0.5; }
 
 // Linearly-implicit Swift-Hohenberg step (sh_linearised.py:51-57):
 //   D = (5U - Uo)^2 k/16 - g k U ;  b = (I + L k/2) U ;  A z = (I + D - L k/2) z

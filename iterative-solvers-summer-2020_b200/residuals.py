@@ -26,8 +26,12 @@ class _DeviceResidual:
 
     problem = None
 
-    def __init__(self, nx, ny, *, comm=None, inner_m=30, outer_k=10, gs="cgs2", gs_tau=2.0 ** -0.5,
+    def __init__(self, nx, ny, *, comm=None, inner_m=30, outer_k=10, gs="cgs-ifneeded", gs_tau=0.25,
                  kernel_variant=0, buffers=None):
+        # gs: Gram-Schmidt variant of the Arnoldi process.  SciPy uses modified GS (j dependent reductions per
+        # step); the device path batches all dots of a step into one fused reduction (classical GS) and takes a
+        # second pass only when ||w_after|| < gs_tau ||w_before|| (cancellation of more than 1/gs_tau), decided on
+        # the device.  "cgs2" always re-orthogonalises, "cgs" never does.
         self.nx, self.ny = int(nx), int(ny)
         self.comm = comm
         self._krylov = (int(inner_m), int(outer_k))
@@ -147,11 +151,17 @@ class SHResidual(_DeviceResidual):
         ctx.check(getattr(ctx.lib, fn)(ctx.handle, ctx.buf.ptr(dx), ctx.buf.ptr(dy)))
         return ctx.buf.to_user(dy, x)
 
-    def steps(self, U, nsteps=1, history=None, **opts):
+    def steps(self, U, nsteps=1, history=None, inplace=False, **opts):
         """``nsteps`` implicit time steps of the script's loop (sh_scipy_nk.py:53-61), entirely on the device:
-        ``Uo = U; U = newton_krylov(residual, Uo, **opts)``.  Returns the new field like ``U``."""
+        ``Uo = U; U = newton_krylov(residual, Uo, **opts)``.  Returns the new field like ``U``.
+        ``inplace=True`` advances a flat fp64 device buffer without any copy (and returns it)."""
         ctx = self.context()
-        du = ctx.vec(U, "U")
+        if inplace:
+            du = U
+            if du.shape[0] != ctx.n:
+                raise ValueError(f"U has {du.shape[0]} elements, expected {ctx.n}")
+        else:
+            du = ctx.vec(U, "U")
         o = Context.make_opts(**opts)
         hists = [HistoryBuffer() for _ in range(nsteps)]
         arr = (_capi.History * nsteps)(*[h.c for h in hists])
@@ -162,8 +172,22 @@ class SHResidual(_DeviceResidual):
             history.extend(h.as_dict() for h in hists)
         self._prev = None  # the engine's per-step constant now belongs to the last step
         if rc != _capi.OK:
-            ctx.check(rc, ctx.buf.to_user(du, U))
-        return ctx.buf.to_user(du, U)
+            ctx.check(rc, du if inplace else ctx.buf.to_user(du, U))
+        return du if inplace else ctx.buf.to_user(du, U)
+
+    def profile(self, on=True):
+        """switch the per-kernel-class CUDA-event timing of the engine on / off"""
+        ctx = self.context()
+        ctx.check(ctx.lib.jfnk_profile_enable(ctx.handle, 1 if on else 0))
+
+    def profile_read(self):
+        """{class: {"launches", "ms", "bytes"}} since the last read (synchronises the stream)"""
+        ctx = self.context()
+        arr = (_capi.KernelStat * 32)()
+        cnt = C.c_int(0)
+        ctx.check(ctx.lib.jfnk_profile_read(ctx.handle, arr, 32, C.byref(cnt)))
+        return {arr[i].name.decode(): {"launches": int(arr[i].launches), "ms": float(arr[i].ms), "bytes": float(arr[i].bytes)}
+                for i in range(cnt.value)}
 
 
 class SHLinearised(_DeviceResidual):

@@ -130,3 +130,18 @@ class SHLinearisedOracle:
         for _ in range(nsteps):
             U, Uo = self.step(U, Uo)
         return U
+
+
+def apply_lap_roll(u, N, h):
+    """Periodic 5-point Laplacian by np.roll -- the same operator as build_lap without forming a matrix; used
+    where the CSR build is too large (checked against the matrices in tests/test_oracle.py)."""
+    e = 1 / h**2
+    U = np.asarray(u).reshape(N, N)
+    out = e * (np.roll(U, 1, 0) + np.roll(U, -1, 0) + np.roll(U, 1, 1) + np.roll(U, -1, 1)) - 4 * e * U
+    return out.reshape(-1)
+
+
+def apply_L_roll(u, N, h, r):
+    """L u = -Lap(Lap u) - 2 Lap u + (r-1) u by two roll-Laplacians (sh_scipy_nk.py:39 without the matrix)."""
+    lu = apply_lap_roll(u, N, h)
+    return -apply_lap_roll(lu, N, h) - 2 * lu + (r - 1) * np.asarray(u).reshape(-1)
