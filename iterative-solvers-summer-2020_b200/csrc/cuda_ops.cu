@@ -248,14 +248,14 @@ class CudaOps : public DeviceOps {
     top = t; bot = b;
   }
 
-  bool use_march(const ShArgs& A) const {
+  bool use_tma(const ShArgs& A) const {
     if (variant_ == 1) return false;
     bool ok = (g_.nx % 2 == 0) && aligned16(A.x) && aligned16(A.xtop) && aligned16(A.xbot) && aligned16(A.out) &&
               (!A.v || (aligned16(A.v) && aligned16(A.vtop) && aligned16(A.vbot))) && (!A.d || aligned16(A.d)) &&
               (!A.f0 || aligned16(A.f0)) && (!A.out2 || aligned16(A.out2));
     if (!ok) return false;
     if (variant_ == 2) return true;
-    return g_.nx >= 128 && g_.nrows >= 32; // small grids are launch-latency bound: one thread per point
+    return g_.nx >= 256 && g_.nrows >= 32; // small grids are launch-latency bound: one thread per point
   }
 
   template <int OP, bool HAS_V>
@@ -268,20 +268,23 @@ class CudaOps : public DeviceOps {
                       : OP == OP_RESID ? (3.0 + (HAS_V ? 1.0 : 0.0) + (A.out2 ? 1.0 : 0.0))
                       : OP == OP_JVP ? 5.0 : OP == OP_LINPREP ? 4.0 : 3.0;
     Prof prof(this, cls, nb(vecs));
-    if (use_march(A)) {
-      int strips = (g_.nx + 63) / 64;
-      long long target = (long long)sms_ * 16; // warps wanted in flight
-      long long ry = ((long long)g_.nrows * strips) / target;
-      if (ry < 8) ry = 8;
-      if (ry > 64) ry = 64;
-      if (ry > g_.nrows) ry = g_.nrows;
-      A.ry = (int)ry;
-      long long chunks = (g_.nrows + ry - 1) / ry;
-      long long warps = chunks * strips;
-      int blocks = (int)((warps + kMarchWarps - 1) / kMarchWarps);
-      sh_march_kernel<OP, HAS_V><<<blocks, kMarchWarps * 32, 0, stream_>>>(A, shp_, S_, ws_);
+    if (use_tma(A)) {
+      using LY = TmaLayout<OP, HAS_V>;
+      static int ctas_per_sm = 0; // per instantiation: opt in to the large dynamic shared memory once
+      if (ctas_per_sm == 0) {
+        ck(cudaFuncSetAttribute(sh_tma_kernel<OP, HAS_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LY::kSmemBytes),
+           "cudaFuncSetAttribute(smem)");
+        int nb_ = 0;
+        ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, sh_tma_kernel<OP, HAS_V>, kTmaThreads, LY::kSmemBytes),
+           "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+        ctas_per_sm = nb_ > 0 ? nb_ : 1;
+      }
+      // persistent grid: every CTA resident, each owning an equal contiguous range of strip-rows (>= 16 rows)
+      long long total = (long long)((g_.nx + kTmaTX - 1) / kTmaTX) * g_.nrows;
+      long long blocks = std::min<long long>((long long)sms_ * ctas_per_sm, std::max<long long>(1, total / 16));
+      if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+      sh_tma_kernel<OP, HAS_V><<<(int)blocks, kTmaThreads, LY::kSmemBytes, stream_>>>(A, shp_, S_, ws_);
     } else {
-      A.ry = 0;
       int blocks = stream_grid(g_.n(), 256);
       sh_point_kernel<OP, HAS_V><<<blocks, 256, 0, stream_>>>(A, shp_, S_, ws_);
     }

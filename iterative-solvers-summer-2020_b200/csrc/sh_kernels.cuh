@@ -3,12 +3,17 @@
 // finite-difference Jacobian-vector product and the norms fused into the same pass.
 //
 // Two kernels share one arithmetic core (sh_value):
-//  * sh_march_kernel -- the product path for large even grids.  Each warp owns a 64-column strip
-//    (one double2 per lane) and marches down a chunk of rows.  A row is read from HBM exactly once per
-//    chunk with coalesced 128-bit loads; the horizontal neighbours travel through a double-buffered
-//    shared-memory row (one __syncwarp per row, no block barrier), the vertical neighbours stay in a
-//    register window (5 rows of u, the horizontal pair sums of 4 rows).  The input combination
-//    t = x + a v of the JVP / line search is formed at load time, so F(x0 + sc z) never exists in memory.
+//  * sh_tma_kernel -- the product path for large even grids: a persistent, warp-specialised marching
+//    kernel.  Each CTA owns a contiguous run of rows of a 256-column strip (the global list of
+//    strip-rows is cut into equal contiguous ranges, one per resident CTA, so the load balance is exact
+//    and only 4 warm-up rows per run are read twice).  One producer thread streams whole rows (strip +
+//    2 halo columns per side; operand rows x, v and the pointwise rows d, f0) from HBM into a
+//    multi-stage shared-memory ring with TMA bulk copies (cp.async.bulk, completion on mbarriers);
+//    four consumer warps (one double2 per thread) read their columns and horizontal neighbours straight
+//    from the staged row, keep the vertical neighbours in a register window (5 rows of u, the horizontal
+//    pair sums of 4 rows) and write the result with coalesced 128-bit stores.  Every input row is read
+//    from HBM once; the input combination t = x + a v of the JVP / line search is formed when the row is
+//    consumed, so F(x0 + sc z) never exists in memory.
 //  * sh_point_kernel -- one thread per grid point straight from global memory; used for small / odd
 //    grids (61 x 61, 91 x 61 ...) where launch latency, not bandwidth, is the bound, and as an independent
 //    cross-check of the marching kernel in the parity tests (kernel_variant = 1).
@@ -33,7 +38,6 @@ struct ShArgs {
   double* out2;                  // RESID: x + a v (may be null) ; LINPREP: D
   int nx, nrows;
   int norm_off;                  // RESID: S[norm_off..+2] = sum F^2, max|F|, max|t|
-  int ry;                        // marching kernel: rows per chunk
 };
 
 __device__ __forceinline__ const double* sh_row(const double* base, const double* top, const double* bot, int r, int nx,
@@ -124,93 +128,188 @@ __global__ void __launch_bounds__(256) sh_point_kernel(ShArgs A, SHParams P, dou
   }
 }
 
+
 // ---------------------------------------------------------------------------------------------------
-// marching kernel: warp = 64-column strip x ry rows
+// TMA-pipelined marching kernel
 // ---------------------------------------------------------------------------------------------------
-constexpr int kMarchWarps = 4;
+constexpr int kTmaTX = 256;        // columns per strip = 2 per consumer thread
+constexpr int kTmaConsumers = 128; // 4 consumer warps
+constexpr int kTmaThreads = kTmaConsumers + 32; // + 1 producer warp (one elected lane issues the copies)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 template <int OP, bool HAS_V>
-__global__ void __launch_bounds__(kMarchWarps * 32) sh_march_kernel(ShArgs A, SHParams P, double* S, ReduceWs ws) {
-  __shared__ __align__(16) double smrow[kMarchWarps][2][72];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nx = A.nx, nrows = A.nrows, ry = A.ry;
-  const int strips = (nx + 63) >> 6;
-  const int chunks = (nrows + ry - 1) / ry;
-  const long long wid = (long long)blockIdx.x * kMarchWarps + warp;
-  const bool wact = wid < (long long)strips * chunks;
-  const int strip = wact ? (int)(wid % strips) : 0;
-  const int chunk = wact ? (int)(wid / strips) : 0;
-  const int xs = strip << 6;
-  const int W = min(64, nx - xs); // even
-  const int y0 = chunk * ry, y1 = min(y0 + ry, nrows);
-  const bool act = wact && (2 * lane < W);
-  const bool hact = wact && lane == 0;
-  const int c = xs + 2 * lane;
-  const int cl = xs - 2 < 0 ? xs - 2 + nx : xs - 2;
-  const int cr = xs + W >= nx ? xs + W - nx : xs + W;
-  const double a = HAS_V ? eval_sref(S, A.a) : 0.0;
-  const double scale = sh_scale<OP>(A, S);
-  ShAcc acc = {0.0, 0.0, 0.0};
+struct TmaLayout {
+  static constexpr bool kHasD = (OP == OP_RESID || OP == OP_JVP || OP == OP_LINMV);
+  static constexpr bool kHasF = (OP == OP_JVP || OP == OP_LINPREP);
+  static constexpr int kX = 0;                                  // offsets in doubles inside one stage
+  static constexpr int kV = kTmaTX + 4;
+  static constexpr int kD = kV + (HAS_V ? kTmaTX + 4 : 0);
+  static constexpr int kF = kD + (kHasD ? kTmaTX : 0);
+  static constexpr int kStageDoubles = kF + (kHasF ? kTmaTX : 0);
+  static constexpr int kStages = (kStageDoubles * 8 > 6000) ? 8 : (kStageDoubles * 8 > 3000 ? 12 : 16);
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageDoubles * 8 + 2 * kStages * sizeof(uint64_t);
+};
 
-  auto load2 = [&](int r, int col) -> double2 {
-    double2 t = ldg2(sh_row(A.x, A.xtop, A.xbot, r, nx, nrows) + col);
-    if (HAS_V) {
-      double2 vv = ldg2(sh_row(A.v, A.vtop, A.vbot, r, nx, nrows) + col);
-      t.x = combine(t.x, a, vv.x);
-      t.y = combine(t.y, a, vv.y);
+struct TmaWork {
+  long long begin, end; // this CTA's range of global strip-row indices (strip-major: idx = strip*nrows + row)
+};
+
+template <int OP, bool HAS_V>
+__global__ void __launch_bounds__(kTmaThreads) sh_tma_kernel(ShArgs A, SHParams P, double* S, ReduceWs ws) {
+  using LY = TmaLayout<OP, HAS_V>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stage0 = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)LY::kStages * LY::kStageDoubles * 8);
+  uint64_t* empty = full + LY::kStages;
+
+  const int nx = A.nx, nrows = A.nrows;
+  const int strips = (nx + kTmaTX - 1) / kTmaTX;
+  const long long total = (long long)strips * nrows;
+  const long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LY::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTmaConsumers / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  ShAcc acc = {0.0, 0.0, 0.0};
+  if (warp == kTmaConsumers / 32) {
+    // ------------------------------- producer: one lane streams rows into the ring -----------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      long long idx = begin;
+      while (idx < end) {
+        const int strip = (int)(idx / nrows), r0 = (int)(idx - (long long)strip * nrows);
+        const long long run_end = min(end, (long long)(strip + 1) * nrows);
+        const int r1 = r0 + (int)(run_end - idx);
+        const int xs = strip * kTmaTX, W = min(kTmaTX, nx - xs);
+        const int cl = xs - 2 < 0 ? xs - 2 + nx : xs - 2, cr = xs + W >= nx ? xs + W - nx : xs + W;
+        for (int ra = r0 - 2; ra < r1 + 2; ++ra) {
+          const int y = ra - 2;
+          const bool pt = y >= r0;
+          mbar_wait(&empty[s], ph ^ 1u);
+          double* st = stage0 + (size_t)s * LY::kStageDoubles;
+          uint32_t bytes = (uint32_t)(W + 4) * 8u * (HAS_V ? 2u : 1u);
+          if (pt) bytes += (uint32_t)W * 8u * ((LY::kHasD ? 1u : 0u) + (LY::kHasF ? 1u : 0u));
+          mbar_expect_tx(&full[s], bytes);
+          {
+            const double* row = sh_row(A.x, A.xtop, A.xbot, ra, nx, nrows);
+            tma_load(st + LY::kX, row + cl, 16u, &full[s]);
+            tma_load(st + LY::kX + 2, row + xs, (uint32_t)W * 8u, &full[s]);
+            tma_load(st + LY::kX + 2 + W, row + cr, 16u, &full[s]);
+          }
+          if (HAS_V) {
+            const double* row = sh_row(A.v, A.vtop, A.vbot, ra, nx, nrows);
+            tma_load(st + LY::kV, row + cl, 16u, &full[s]);
+            tma_load(st + LY::kV + 2, row + xs, (uint32_t)W * 8u, &full[s]);
+            tma_load(st + LY::kV + 2 + W, row + cr, 16u, &full[s]);
+          }
+          if (pt) {
+            const size_t e = (size_t)y * nx + xs;
+            if (LY::kHasD) tma_load(st + LY::kD, A.d + e, (uint32_t)W * 8u, &full[s]);
+            if (LY::kHasF) tma_load(st + LY::kF, A.f0 + e, (uint32_t)W * 8u, &full[s]);
+          }
+          if (++s == LY::kStages) { s = 0; ph ^= 1u; }
+        }
+        idx = run_end;
+      }
     }
-    return t;
-  };
-  const double2 zero2 = make_double2(0.0, 0.0);
-  double2 u0 = zero2, u1 = zero2, u2 = zero2, u3 = zero2, u4 = zero2;
-  double2 p0 = zero2, p1 = zero2, p2 = zero2, p3 = zero2; // horizontal +-1 pair sums, rows ra-3..ra
-  double2 q0 = zero2, q1 = zero2, q2 = zero2;             // horizontal +-2 pair sums, rows ra-2..ra
-  // software pipeline: row ra+1 is in flight while row ra is exchanged and consumed
-  double2 nown = zero2, nhl = zero2, nhr = zero2;
-  if (act) nown = load2(y0 - 2, c);
-  if (hact) { nhl = load2(y0 - 2, cl); nhr = load2(y0 - 2, cr); }
-  for (int ra = y0 - 2; ra < y1 + 2; ++ra) {
-    double2 own = nown, hl = nhl, hr = nhr;
-    if (ra + 1 < y1 + 2) {
-      if (act) nown = load2(ra + 1, c);
-      if (hact) { nhl = load2(ra + 1, cl); nhr = load2(ra + 1, cr); }
-    }
-    const int y = ra - 2;
-    const bool emit = act && y >= y0;
-    const size_t e = (size_t)(emit ? y : 0) * nx + c;
-    // operands of the output row: issue their loads before the exchange so they overlap it
-    double2 dv = zero2, fv = zero2;
-    if (emit) {
-      if (OP == OP_RESID || OP == OP_JVP || OP == OP_LINMV) dv = ldg2(A.d + e);
-      if (OP == OP_JVP || OP == OP_LINPREP) fv = ldg2(A.f0 + e);
-    }
-    double* s = smrow[warp][(ra - y0) & 1];
-    if (act) *reinterpret_cast<double2*>(s + 2 + 2 * lane) = own;
-    if (hact) {
-      *reinterpret_cast<double2*>(s) = hl;
-      *reinterpret_cast<double2*>(s + 2 + W) = hr;
-    }
-    __syncwarp();
-    double2 L = zero2, R = zero2;
-    if (act) {
-      L = *reinterpret_cast<const double2*>(s + 2 * lane);
-      R = *reinterpret_cast<const double2*>(s + 4 + 2 * lane);
-    }
-    u0 = u1; u1 = u2; u2 = u3; u3 = u4; u4 = own;
-    p0 = p1; p1 = p2; p2 = p3;
-    p3.x = L.y + own.y; p3.y = own.x + R.x;
-    q0 = q1; q1 = q2;
-    q2.x = L.x + R.x; q2.y = L.y + R.y;
-    if (emit) {
-      // rows: u0..u4 = y-2..y+2 ; p0,p1,p2 = pair sums of rows y-1,y,y+1 ; q0 = +-2 pair sum of row y
-      double s1x = p1.x + u1.x + u3.x, s1y = p1.y + u1.y + u3.y;
-      double sdx = p0.x + p2.x, sdy = p0.y + p2.y;
-      double s2x = q0.x + u0.x + u4.x, s2y = q0.y + u0.y + u4.y;
-      double2 o, o2 = zero2;
-      o.x = sh_value<OP>(P, scale, u2.x, s1x, sdx, s2x, dv.x, fv.x, o2.x, acc);
-      o.y = sh_value<OP>(P, scale, u2.y, s1y, sdy, s2y, dv.y, fv.y, o2.y, acc);
-      stg2(A.out + e, o);
-      if ((OP == OP_RESID && A.out2) || OP == OP_LINPREP) stg2(A.out2 + e, o2);
+  } else {
+    // ------------------------------- consumers: 2 columns per thread ----------------------------------
+    const double a = HAS_V ? eval_sref(S, A.a) : 0.0;
+    const double scale = sh_scale<OP>(A, S);
+    const int t2 = 2 * threadIdx.x; // column offset inside the strip
+    const double2 zero2 = make_double2(0.0, 0.0);
+    int s = 0;
+    uint32_t ph = 0;
+    long long idx = begin;
+    while (idx < end) {
+      const int strip = (int)(idx / nrows), r0 = (int)(idx - (long long)strip * nrows);
+      const long long run_end = min(end, (long long)(strip + 1) * nrows);
+      const int r1 = r0 + (int)(run_end - idx);
+      const int xs = strip * kTmaTX, W = min(kTmaTX, nx - xs);
+      const bool act = t2 < W;
+      double2 u0 = zero2, u1 = zero2, u2 = zero2, u3 = zero2, u4 = zero2;
+      double2 p0 = zero2, p1 = zero2, p2 = zero2, p3 = zero2; // horizontal +-1 pair sums, rows ra-3..ra
+      double2 q0 = zero2, q1 = zero2, q2 = zero2;             // horizontal +-2 pair sums, rows ra-2..ra
+      for (int ra = r0 - 2; ra < r1 + 2; ++ra) {
+        const int y = ra - 2;
+        mbar_wait(&full[s], ph);
+        const double* st = stage0 + (size_t)s * LY::kStageDoubles;
+        double2 L = zero2, own = zero2, R = zero2, dv = zero2, fv = zero2;
+        if (act) {
+          const double* sx = st + LY::kX + t2;
+          L = *reinterpret_cast<const double2*>(sx);
+          own = *reinterpret_cast<const double2*>(sx + 2);
+          R = *reinterpret_cast<const double2*>(sx + 4);
+          if (HAS_V) {
+            const double* sv = st + LY::kV + t2;
+            double2 vl = *reinterpret_cast<const double2*>(sv);
+            double2 vo = *reinterpret_cast<const double2*>(sv + 2);
+            double2 vr = *reinterpret_cast<const double2*>(sv + 4);
+            L.x = combine(L.x, a, vl.x); L.y = combine(L.y, a, vl.y);
+            own.x = combine(own.x, a, vo.x); own.y = combine(own.y, a, vo.y);
+            R.x = combine(R.x, a, vr.x); R.y = combine(R.y, a, vr.y);
+          }
+          if (y >= r0) {
+            if (LY::kHasD) dv = *reinterpret_cast<const double2*>(st + LY::kD + t2);
+            if (LY::kHasF) fv = *reinterpret_cast<const double2*>(st + LY::kF + t2);
+          }
+        }
+        // this warp is done with the stage: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == LY::kStages) { s = 0; ph ^= 1u; }
+
+        u0 = u1; u1 = u2; u2 = u3; u3 = u4; u4 = own;
+        p0 = p1; p1 = p2; p2 = p3;
+        p3.x = L.y + own.y; p3.y = own.x + R.x;
+        q0 = q1; q1 = q2;
+        q2.x = L.x + R.x; q2.y = L.y + R.y;
+        if (act && y >= r0) {
+          // rows: u0..u4 = y-2..y+2 ; p0,p1,p2 = pair sums of rows y-1,y,y+1 ; q0 = +-2 pair sum of row y
+          double s1x = p1.x + u1.x + u3.x, s1y = p1.y + u1.y + u3.y;
+          double sdx = p0.x + p2.x, sdy = p0.y + p2.y;
+          double s2x = q0.x + u0.x + u4.x, s2y = q0.y + u0.y + u4.y;
+          const size_t e = (size_t)y * nx + xs + t2;
+          double2 o, o2 = zero2;
+          o.x = sh_value<OP>(P, scale, u2.x, s1x, sdx, s2x, dv.x, fv.x, o2.x, acc);
+          o.y = sh_value<OP>(P, scale, u2.y, s1y, sdy, s2y, dv.y, fv.y, o2.y, acc);
+          stg2(A.out + e, o);
+          if ((OP == OP_RESID && A.out2) || OP == OP_LINPREP) stg2(A.out2 + e, o2);
+        }
+      }
+      idx = run_end;
     }
   }
   if (OP == OP_RESID) {
