@@ -1,0 +1,82 @@
+"""Pin the CPU oracle (oracle/) against golden vectors produced by the REFERENCE's own modules
+(tests/golden/make_golden.py, run in the build container) and against the reference's sparse matrices."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.mesh import DropletOracle, PMA2Oracle
+from oracle.sh import SHOracle, apply_L_roll, apply_lap_roll, seeded_state, sh13_coefficients
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def relmax(a, b):
+    return np.abs(np.ravel(a) - np.ravel(b)).max() / max(np.abs(np.ravel(b)).max(), 1e-300)
+
+
+def test_sh_operator_structure():
+    """the 13-point coefficients and storage facts SURVEY.md section 8 (a1) states for the reference's matrices"""
+    o = SHOracle(N=64)
+    assert o.L.format == "csr" and o.L.nnz == 13 * 64 * 64 and o.Lap.nnz == 5 * 64 * 64
+    c0, c1, c2, c3 = sh13_coefficients(o.h, o.r)
+    row = o.L.getrow(5 * 64 + 7).toarray().ravel()
+    assert np.isclose(row[5 * 64 + 7], c0) and np.isclose(row[5 * 64 + 8], c1)
+    assert np.isclose(row[6 * 64 + 8], c2) and np.isclose(row[7 * 64 + 7], c3)
+    np.testing.assert_allclose([c0, c1, c2, c3], [-111.582, 47.3088, -13.1072, -6.5536], rtol=1e-12)
+    u = seeded_state(64, 3)
+    assert relmax(apply_L_roll(u, 64, o.h, o.r), o.L @ u) < 1e-14
+    assert relmax(apply_lap_roll(u, 64, o.h), o.Lap @ u) < 1e-14
+
+
+def test_sh_oracle_is_deterministic():
+    o = SHOracle(N=32, d=20.0)
+    U0 = seeded_state(32)
+    a = o.run(U0, 3)
+    b = SHOracle(N=32, d=20.0).run(U0, 3)
+    assert np.array_equal(a, b)
+
+
+def test_pma2_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, "pma2_n51.npz"))
+    o = PMA2Oracle(N=51)
+    o.set_mesh(g["op_Q"])
+    for key, ref in (("d2ksi", "op_d2ksi"), ("d2eta", "op_d2eta"), ("dksideta", "op_dksideta"), ("J", "op_J")):
+        assert np.array_equal(o.met[key], g[ref]), key
+    vxx, vyy = o.ops.laplace_of(g["op_u"], o.met)
+    assert np.array_equal(vxx, g["op_vxx"]) and np.array_equal(vyy, g["op_vyy"])
+    o.set_prev(g["op_Uval"])
+    assert np.array_equal(o.CN, g["op_CN"])
+    assert np.array_equal(o.residual(g["op_u"]), g["op_residual"])
+    # the script's own run: three passes of the time loop including the DCT mesh update
+    o2 = PMA2Oracle(N=51)
+    U = np.zeros(51 * 51)
+    for s in range(3):
+        U = o2.step(U)
+        assert np.array_equal(U, g[f"run_U{s}"]), s
+        assert np.array_equal(o2.Q, g[f"run_Q{s}"]), s
+
+
+def test_droplet_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, "droplet_91x61.npz"))
+    o = DropletOracle()
+    o.set_mesh(g["state_Q"])
+    for key, ref in (("d2ksi", "op_d2ksi"), ("d2eta", "op_d2eta"), ("dksideta", "op_dksideta"), ("J", "op_J")):
+        assert np.array_equal(o.met[key], g[ref]), key
+    o.set_prev(g["state_U"], 1e-4)
+    assert np.array_equal(o.Uxx, g["op_Uxx"]) and np.array_equal(o.Uyy, g["op_Uyy"])
+    assert np.array_equal(o.PI(g["state_U"]), g["op_PI"])
+    assert np.array_equal(o.F, g["op_F"])
+    vxx, vyy = o.ops.laplace_of(g["op_u"], o.met)
+    assert np.array_equal(vxx, g["op_vxx"]) and np.array_equal(vyy, g["op_vyy"])
+    assert np.array_equal(o.residual(g["op_u"]), g["op_residual"])
+    # two passes of evolve_with_PDE's loop body incl. loop_pma(3e-9, 400)
+    o2 = DropletOracle()
+    o2.Q = g["state_Q"].copy()
+    U = g["state_U"].copy()
+    for s in range(2):
+        hist = []
+        U = o2.step(U, 1e-4, history=hist)
+        assert np.array_equal(U, g[f"run_U{s}"]), s
+        assert np.array_equal(o2.Q, g[f"run_Q{s}"]), s
+        assert np.allclose([h[0] for h in hist[0]["iters"]], g[f"run_hist{s}"], rtol=0, atol=0)
