@@ -9,29 +9,45 @@
 namespace jfnk {
 
 // out[i] = V_i . w (i < nv), out[nv] = w . w
-template <int NV>
-__global__ void __launch_bounds__(256) mdot_kernel(PtrList V, int nv, const double* __restrict__ w, size_t n,
-                                                   double* S, int out_off, int guard, double tau2, ReduceWs ws) {
+// NV = accumulators compiled in (nv <= NV at run time), U = double2 elements per thread per sweep: few basis
+// vectors -> several elements per thread so that every thread still keeps >= 8 independent 128-bit loads in flight.
+// (two 256-thread CTAs per SM: <= 128 registers, checked with -Xptxas -v; one CTA/SM starves the memory pipe)
+template <int NV, int U>
+__global__ void __launch_bounds__(256, 2) mdot_kernel(PtrList V, int nv, const double* __restrict__ w, size_t n,
+                                                      double* S, int out_off, int guard, double tau2, ReduceWs ws) {
   if (guard && !gs_second_pass_taken(S, nv, tau2)) return; // grid-uniform
   double acc[NV + 1];
 #pragma unroll
   for (int k = 0; k <= NV; ++k) acc[k] = 0.0;
   const size_t n2 = n >> 1;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-    double2 wv = ldg2(w + 2 * i);
-    // groups of 8 basis vectors: 8 independent 128-bit loads in flight per thread, then 16 FMAs
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n2; i0 += stride * U) {
+    double2 wv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + (size_t)u * stride;
+      wv[u] = (i < n2) ? ldg2(w + 2 * i) : make_double2(0.0, 0.0);
+    }
+    // groups of 8 basis vectors: 8*U independent 128-bit loads in flight per thread, then the FMAs
 #pragma unroll
     for (int kb = 0; kb < NV; kb += 8) {
-      double2 vv[8];
+      double2 vv[U][8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (kb + q < NV && kb + q < nv) vv[q] = ldg2(V.p[kb + q] + 2 * i);
+      for (int u = 0; u < U; ++u) {
+        const size_t i = i0 + (size_t)u * stride;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (kb + q < NV && kb + q < nv) acc[kb + q] = fma(vv[q].y, wv.y, fma(vv[q].x, wv.x, acc[kb + q]));
+        for (int q = 0; q < 8; ++q)
+          if (kb + q < NV && kb + q < nv && i < n2) vv[u][q] = ldg2(V.p[kb + q] + 2 * i);
+          else vv[u][q] = make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (kb + q < NV && kb + q < nv) acc[kb + q] = fma(vv[u][q].y, wv[u].y, fma(vv[u][q].x, wv[u].x, acc[kb + q]));
     }
-    acc[NV] = fma(wv.y, wv.y, fma(wv.x, wv.x, acc[NV]));
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[NV] = fma(wv[u].y, wv[u].y, fma(wv[u].x, wv[u].x, acc[NV]));
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { // odd tail element
     double we = w[n - 1];
@@ -67,55 +83,98 @@ __global__ void __launch_bounds__(256) mdot_scalar_kernel(PtrList V, int nv, con
 // MODE 1: w -= sum_i S[c_off+i] V_i
 // MODE 2: w  = sum_i S[c_off+i] V_i                  (dx assembly; w is write-only)
 // S[n2_off] = ||w||^2 of the result.
-template <int MODE, bool VEC>
-__global__ void __launch_bounds__(256) maxpy_kernel(PtrList V, int nv, double* __restrict__ w, size_t n, double* S,
-                                                    int c_off, int n2_off, int guard, double tau2, ReduceWs ws) {
+// NV = vectors compiled in (nv <= NV at run time; the loop over vectors is fully unrolled so that the vector
+// base pointers come straight from the kernel-parameter constant bank and the loads of a group of 8 vectors are
+// issued back to back), U = double2 elements per thread per sweep.
+template <int MODE, int NV, int U>
+__global__ void __launch_bounds__(256, 2) maxpy_kernel(PtrList V, int nv, double* __restrict__ w, size_t n, double* S,
+                                                       int c_off, int n2_off, int guard, double tau2, ReduceWs ws) {
+  if (guard && !gs_second_pass_taken(S, nv, tau2)) return;
+  __shared__ double c[JF_MAXV];
+  if (threadIdx.x < JF_MAXV) {
+    double cv = 0.0;
+    if (threadIdx.x < nv) {
+      cv = S[c_off + threadIdx.x];
+      if (MODE == 0) cv /= S[JS_VN2 + threadIdx.x];
+    }
+    c[threadIdx.x] = (MODE == 2) ? cv : -cv;
+  }
+  __syncthreads();
+  double acc[1] = {0.0};
+  const size_t n2 = n >> 1;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n2; i0 += stride * U) {
+    double2 t[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + (size_t)u * stride;
+      t[u] = make_double2(0.0, 0.0);
+      if (MODE != 2 && i < n2) t[u] = *reinterpret_cast<const double2*>(w + 2 * i);
+    }
+#pragma unroll
+    for (int kb = 0; kb < NV; kb += 8) {
+      if (kb < nv) {
+        double2 v[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t i = i0 + (size_t)u * stride;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            v[u][q] = make_double2(0.0, 0.0);
+            if (kb + q < NV && kb + q < nv && i < n2) v[u][q] = ldg2(V.p[kb + q] + 2 * i);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (kb + q < NV) {
+            const double ck = c[kb + q]; // 0 beyond nv
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              t[u].x = fma(ck, v[u][q].x, t[u].x);
+              t[u].y = fma(ck, v[u][q].y, t[u].y);
+            }
+          }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + (size_t)u * stride;
+      if (i < n2) {
+        stg2(w + 2 * i, t[u]);
+        acc[0] = fma(t[u].y, t[u].y, fma(t[u].x, t[u].x, acc[0]));
+      }
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { // odd tail element
+    double tt = (MODE == 2) ? 0.0 : w[n - 1];
+    for (int k = 0; k < nv; ++k) tt = fma(c[k], V.p[k][n - 1], tt);
+    w[n - 1] = tt;
+    acc[0] = fma(tt, tt, acc[0]);
+  }
+  grid_reduce<1>(acc, 0u, ws, S + n2_off);
+}
+
+// scalar-load variant for operands that are not 16-byte aligned
+template <int MODE>
+__global__ void __launch_bounds__(256) maxpy_scalar_kernel(PtrList V, int nv, double* __restrict__ w, size_t n, double* S,
+                                                           int c_off, int n2_off, int guard, double tau2, ReduceWs ws) {
   if (guard && !gs_second_pass_taken(S, nv, tau2)) return;
   __shared__ double c[JF_MAXV];
   __shared__ const double* vp[JF_MAXV];
   if (threadIdx.x < nv) {
     double cv = S[c_off + threadIdx.x];
     if (MODE == 0) cv /= S[JS_VN2 + threadIdx.x];
-    c[threadIdx.x] = cv;
+    c[threadIdx.x] = (MODE == 2) ? cv : -cv;
     vp[threadIdx.x] = V.p[threadIdx.x];
   }
   __syncthreads();
   double acc[1] = {0.0};
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  if (VEC) {
-    const size_t n2 = n >> 1;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-      double2 t;
-      int k0 = 0;
-      if (MODE == 2) {
-        double2 v = ldg2(vp[0] + 2 * i);
-        t.x = c[0] * v.x; t.y = c[0] * v.y;
-        k0 = 1;
-      } else {
-        t = *reinterpret_cast<const double2*>(w + 2 * i);
-      }
-#pragma unroll 8
-      for (int k = k0; k < nv; ++k) {
-        double2 v = ldg2(vp[k] + 2 * i);
-        if (MODE == 2) { t.x = fma(c[k], v.x, t.x); t.y = fma(c[k], v.y, t.y); }
-        else { t.x = fma(-c[k], v.x, t.x); t.y = fma(-c[k], v.y, t.y); }
-      }
-      stg2(w + 2 * i, t);
-      acc[0] = fma(t.y, t.y, fma(t.x, t.x, acc[0]));
-    }
-  }
-  // scalar path: everything when !VEC, the odd tail element when VEC
-  {
-    size_t begin = VEC ? (n & ~(size_t)1) : 0;
-    for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      double t;
-      int k0 = 0;
-      if (MODE == 2) { t = c[0] * vp[0][i]; k0 = 1; }
-      else t = w[i];
-      for (int k = k0; k < nv; ++k) t = (MODE == 2) ? fma(c[k], vp[k][i], t) : fma(-c[k], vp[k][i], t);
-      w[i] = t;
-      acc[0] = fma(t, t, acc[0]);
-    }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double t = (MODE == 2) ? 0.0 : w[i];
+    for (int k = 0; k < nv; ++k) t = fma(c[k], vp[k][i], t);
+    w[i] = t;
+    acc[0] = fma(t, t, acc[0]);
   }
   grid_reduce<1>(acc, 0u, ws, S + n2_off);
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -138,17 +139,43 @@ class CudaOps : public DeviceOps {
     if (cap > (size_t)kMaxBlocks) cap = kMaxBlocks;
     return (int)std::min(b, cap);
   }
+  // persistent grid for a grid-stride streaming kernel: exactly the number of CTAs that are resident at once
+  // (148 SMs x occupancy), so there is no partial second wave; fewer when the problem is small
+  template <typename K>
+  int resident_grid(K kernel, int threads, size_t items_per_thread_pass) {
+    static int per_sm = 0; // one static per kernel instantiation
+    if (per_sm == 0) {
+      int nb_ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, kernel, threads, 0) != cudaSuccess || nb_ < 1) nb_ = 1;
+      per_sm = nb_;
+    }
+    long long cap = std::min<long long>((long long)sms_ * per_sm, kMaxBlocks);
+    long long need = (long long)((items_per_thread_pass + threads - 1) / threads);
+    return (int)std::max<long long>(1, std::min(cap, need));
+  }
 
   template <int NV>
   void mdot_launch(bool vec, const PtrList& L, int nv, const double* w, int out_off, int guard, double tau2) {
     size_t n = g_.n();
-    // register-heavy instantiations run fewer, fatter blocks: one or two 256-thread CTAs per SM
-    int blocks = std::min(stream_grid(vec ? n / 2 : n, 256), sms_ * (NV <= 8 ? 8 : (NV <= 16 ? 4 : 2)));
+    constexpr int U = NV <= 4 ? 4 : (NV <= 8 ? 2 : 1);
     Prof prof(this, guard ? K_MDOT2 : K_MDOT, nb(nv + 1)); // pass-2 launches may early-exit on device
-    if (vec) mdot_kernel<NV><<<blocks, 256, 0, stream_>>>(L, nv, w, n, S_, out_off, guard, tau2, ws_);
-    else mdot_scalar_kernel<NV><<<blocks, 256, 0, stream_>>>(L, nv, w, n, S_, out_off, guard, tau2, ws_);
+    if (vec) mdot_kernel<NV, U><<<resident_grid(mdot_kernel<NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, guard, tau2, ws_);
+    else mdot_scalar_kernel<NV><<<resident_grid(mdot_scalar_kernel<NV>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, guard, tau2, ws_);
   }
   void mdot(int nv, const double* const* V, const double* w, int out_off, int guard, double tau2) override {
+    if (nv > 32) {
+      // more than 32 accumulators per thread would drop to one CTA per SM: two passes of <= 24 vectors instead
+      // (w is read twice: +1 of nv+1 vectors).  The first pass parks w.w at out[h]; the second overwrites it.
+      int h = nv / 2;
+      mdot(h, V, w, out_off, guard, tau2);
+      mdot_part(nv - h, nv, V + h, w, out_off + h, guard, tau2);
+      return;
+    }
+    mdot_part(nv, nv, V, w, out_off, guard, tau2);
+  }
+  // nv_guard: the vector count the device-side second-pass predicate refers to (RD[nv_guard] = w.w of pass 1)
+  void mdot_part(int nv, int nv_guard, const double* const* V, const double* w, int out_off, int guard, double tau2) {
+    (void)nv_guard;
     PtrList L;
     bool vec = aligned16(w);
     for (int i = 0; i < nv; ++i) { L.p[i] = V[i]; vec = vec && aligned16(V[i]); }
@@ -161,9 +188,7 @@ class CudaOps : public DeviceOps {
     else if (nv <= 20) mdot_launch<20>(vec, L, nv, w, out_off, guard, tau2);
     else if (nv <= 24) mdot_launch<24>(vec, L, nv, w, out_off, guard, tau2);
     else if (nv <= 28) mdot_launch<28>(vec, L, nv, w, out_off, guard, tau2);
-    else if (nv <= 32) mdot_launch<32>(vec, L, nv, w, out_off, guard, tau2);
-    else if (nv <= 40) mdot_launch<40>(vec, L, nv, w, out_off, guard, tau2);
-    else mdot_launch<JF_MAXV>(vec, L, nv, w, out_off, guard, tau2);
+    else mdot_launch<32>(vec, L, nv, w, out_off, guard, tau2);
   }
 
   template <int MODE>
@@ -173,10 +198,21 @@ class CudaOps : public DeviceOps {
     for (int i = 0; i < nv; ++i) { L.p[i] = V[i]; vec = vec && aligned16(V[i]); }
     for (int i = nv; i < JF_MAXV; ++i) L.p[i] = nullptr;
     size_t n = g_.n();
-    int blocks = stream_grid(vec ? n / 2 : n, 256);
     Prof prof(this, MODE == 2 ? K_MAXPY : (guard ? K_GS_UPDATE2 : K_GS_UPDATE), nb(MODE == 2 ? nv + 1 : nv + 2));
-    if (vec) maxpy_kernel<MODE, true><<<blocks, 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, guard, tau2, ws_);
-    else maxpy_kernel<MODE, false><<<blocks, 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, guard, tau2, ws_);
+    if (!vec) {
+      maxpy_scalar_kernel<MODE><<<resident_grid(maxpy_scalar_kernel<MODE>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, guard, tau2, ws_);
+    } else if (nv <= 4) maxpy_vec<MODE, 4, 4>(L, nv, w, c_off, n2_off, guard, tau2);
+    else if (nv <= 8) maxpy_vec<MODE, 8, 2>(L, nv, w, c_off, n2_off, guard, tau2);
+    else if (nv <= 16) maxpy_vec<MODE, 16, 1>(L, nv, w, c_off, n2_off, guard, tau2);
+    else if (nv <= 24) maxpy_vec<MODE, 24, 1>(L, nv, w, c_off, n2_off, guard, tau2);
+    else if (nv <= 32) maxpy_vec<MODE, 32, 1>(L, nv, w, c_off, n2_off, guard, tau2);
+    else maxpy_vec<MODE, JF_MAXV, 1>(L, nv, w, c_off, n2_off, guard, tau2);
+  }
+  // few vectors -> several elements per thread, so that every thread keeps >= 8 independent loads in flight
+  template <int MODE, int NV, int U>
+  void maxpy_vec(const PtrList& L, int nv, double* w, int c_off, int n2_off, int guard, double tau2) {
+    size_t n = g_.n();
+    maxpy_kernel<MODE, NV, U><<<resident_grid(maxpy_kernel<MODE, NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, guard, tau2, ws_);
   }
   void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int guard, double tau2) override {
     maxpy_launch<0>(nv, V, w, rd_off, n2_off, guard, tau2);
