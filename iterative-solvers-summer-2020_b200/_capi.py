@@ -94,7 +94,7 @@ SIGNATURES = {
 
 def bind(path: str) -> C.CDLL:
     """dlopen ``path`` and attach the prototypes; raises if any declared symbol is missing."""
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res

@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
            "-Xcompiler", "-Wno-unused-function", "-cudart", "static"] + ARCH
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-I", HERE, "-o", LIB] + [os.path.join(HERE, s) for s in SOURCES] + ["-ldl"]
+    cmd += ["-I", HERE, "-o", LIB] + [os.path.join(HERE, s) for s in SOURCES] + ["-ldl", "-Xlinker", "-Bsymbolic"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -21,7 +21,7 @@ def build(force=False):
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")] + [os.path.join(ROOT, "include", "jfnk.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-ffp-contract=off",
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-ffp-contract=off", "-Wl,-Bsymbolic",
            "-I", CSRC, "-o", LIB] + srcs
     subprocess.check_call(cmd)
     return LIB
