@@ -183,6 +183,14 @@ int jfnk_pma2_set_prev(jfnk_ctx* ctx, const double* dUval);
 int jfnk_droplet_setup(jfnk_ctx* ctx, double epsilon, int n_exp, int m_exp, double Bo, double alpha2, double epsilon2);
 int jfnk_droplet_set_prev(jfnk_ctx* ctx, const double* dUval, double dt);
 
+/* Moving-mesh relaxation on the device: `loops` passes of { compute_Q_spatial_ders; J; Laplace_operator(U.val);
+ * compute_and_smooth_monitor; solve_PMA (2-D DCT-II solve); Q += dt_mesh * Q_t } -- loop_pma of droplet.py:590-599
+ * (loops = 400, C = cnorm = 0.15, monitor_mode 0 = |u_xx+u_yy|^2) and the single solve_PMA + explicit update of
+ * PMA2_nk.py:94,103 (loops = 1, cnorm = 1, monitor_mode 1 = 1/(1+u)^6 when epsilon == 0).  dQ_inout is advanced in
+ * place; dUval is the OLD solution (U.val), as in the scripts.  Afterwards call jfnk_mesh_set_potential again. */
+int jfnk_mesh_relax(jfnk_ctx* ctx, double* dQ_inout, const double* dUval, double dt_mesh, int loops, double alpha,
+                    double gamma, double cnorm, int smoothing_iters, int monitor_mode);
+
 /* ---- introspection for benches / tests --------------------------------------------------------- */
 /* number of kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t jfnk_launch_count(jfnk_ctx* ctx);

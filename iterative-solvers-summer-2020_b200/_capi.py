@@ -84,6 +84,7 @@ SIGNATURES = {
     "jfnk_pma2_set_prev": (C.c_int, [_CTX, _P]),
     "jfnk_droplet_setup": (C.c_int, [_CTX, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
     "jfnk_droplet_set_prev": (C.c_int, [_CTX, _P, C.c_double]),
+    "jfnk_mesh_relax": (C.c_int, [_CTX, _P, _P, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]),
     "jfnk_launch_count": (C.c_int64, [_CTX]),
     "jfnk_profile_enable": (C.c_int, [_CTX, C.c_int]),
     "jfnk_profile_read": (C.c_int, [_CTX, C.POINTER(KernelStat), C.c_int, C.POINTER(C.c_int)]),

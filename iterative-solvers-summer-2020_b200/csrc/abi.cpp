@@ -185,6 +185,15 @@ int jfnk_droplet_set_prev(jfnk_ctx* ctx, const double* dUval, double dt) {
   JF_TRY JF_CHECK_CTX(ctx); return done(ctx, ctx->eng->droplet_set_prev(dUval, dt)); JF_CATCH
 }
 
+int jfnk_mesh_relax(jfnk_ctx* ctx, double* dQ_inout, const double* dUval, double dt_mesh, int loops, double alpha,
+                    double gamma, double cnorm, int smoothing_iters, int monitor_mode) {
+  JF_TRY JF_CHECK_CTX(ctx);
+  PmaParams pp; pp.alpha = alpha; pp.gamma = gamma; pp.cnorm = cnorm; pp.smoothing_iters = smoothing_iters;
+  pp.monitor_mode = monitor_mode;
+  return done(ctx, ctx->eng->mesh_relax(dQ_inout, dUval, dt_mesh, loops, pp));
+  JF_CATCH
+}
+
 int jfnk_profile_enable(jfnk_ctx* ctx, int on) {
   JF_CHECK_CTX(ctx);
   ctx->ops->profile_enable(on != 0);

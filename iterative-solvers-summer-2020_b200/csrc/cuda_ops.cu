@@ -6,12 +6,14 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
 #include "backend.h"
 #include "blas_kernels.cuh"
 #include "mesh_kernels.cuh"
+#include "pma_kernels.cuh"
 #include "nccl_dl.h"
 #include "sh_kernels.cuh"
 
@@ -57,6 +59,8 @@ class CudaOps : public DeviceOps {
     for (auto& r : recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : free_events_) cudaEventDestroy(e);
     for (int i = 0; i < 6; ++i) if (halo_[i]) cudaFree(halo_[i]);
+    if (dctx_) cudaFree(dctx_);
+    if (dcty_) cudaFree(dcty_);
     if (pinned_) cudaFreeHost(pinned_);
     if (ws_.ticket) cudaFree(ws_.ticket);
     if (ws_.partials) cudaFree(ws_.partials);
@@ -143,7 +147,8 @@ class CudaOps : public DeviceOps {
   // (148 SMs x occupancy), so there is no partial second wave; fewer when the problem is small
   template <typename K>
   int resident_grid(K kernel, int threads, size_t items_per_thread_pass) {
-    static int per_sm = 0; // one static per kernel instantiation
+    // occupancy per kernel instantiation, keyed by the function address (instantiations share a pointer TYPE)
+    int& per_sm = occupancy_[reinterpret_cast<const void*>(kernel)];
     if (per_sm == 0) {
       int nb_ = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, kernel, threads, 0) != cudaSuccess || nb_ < 1) nb_ = 1;
@@ -434,6 +439,52 @@ class CudaOps : public DeviceOps {
     droplet_combine_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(g_.n(), dp, u, uval, F2, Fprev, F, S_, norm_off, ws_);
   }
 
+  // ---- moving-mesh relaxation ------------------------------------------------------------------------------
+  void pma_monitor(int mode, const double* u, const double* lap, double* out) override {
+    Prof prof(this, K_MESH, nb(mode == 1 ? 2 : 2));
+    pma_monitor_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(g_.n(), mode, u, lap, out);
+  }
+  void pma_smooth(const MeshParams& mp, const double* in, double* out) override {
+    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    Prof prof(this, K_MESH, nb(2));
+    pma_smooth_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, in, out);
+  }
+  void pma_wsum(const double* mon, const double* J, int out_off) override {
+    Prof prof(this, K_MESH, nb(2));
+    pma_wsum_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(g_.n(), mon, J, S_, out_off, ws_);
+  }
+  void pma_rhs(const double* mon, const double* J, ScalarRef add, double alpha, double* out) override {
+    Prof prof(this, K_MESH, nb(3));
+    pma_rhs_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(g_.n(), mon, J, add, alpha, S_, out);
+  }
+  void gemm(int M, int N, int K, const double* A, int ta, const double* B, int tb, double* C) {
+    dim3 grid((N + 15) / 16, (M + 15) / 16);
+    Prof prof(this, K_MESH, 8.0 * ((double)M * K + (double)K * N + (double)M * N));
+    small_gemm_kernel<<<grid, 256, 0, stream_>>>(M, N, K, A, ta, B, tb, C);
+  }
+  void pma_dct2(const double* in, double* tmp, double* out, int inverse) override {
+    const int nx = g_.nx, ny = g_.ny;
+    if (!dctx_) {
+      if (!ck(cudaMalloc(&dctx_, sizeof(double) * (size_t)nx * nx), "cudaMalloc(dct)")) return;
+      if (!ck(cudaMalloc(&dcty_, sizeof(double) * (size_t)ny * ny), "cudaMalloc(dct)")) return;
+      dct_matrix_kernel<<<stream_grid((size_t)nx * nx, 256), 256, 0, stream_>>>(nx, dctx_);
+      dct_matrix_kernel<<<stream_grid((size_t)ny * ny, 256), 256, 0, stream_>>>(ny, dcty_);
+      launches_ += 2;
+    }
+    if (!inverse) {
+      gemm(ny, nx, ny, dcty_, 0, in, 0, tmp);  // Cy . X
+      gemm(ny, nx, nx, tmp, 0, dctx_, 1, out); // . Cx^T
+    } else {
+      gemm(ny, nx, ny, dcty_, 1, in, 0, tmp);  // Cy^T . Y
+      gemm(ny, nx, nx, tmp, 0, dctx_, 0, out); // . Cx
+    }
+  }
+  void pma_spectral_divide(const MeshParams& mp, double gamma, double* Y) override {
+    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    Prof prof(this, K_MESH, nb(2));
+    pma_divide_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, gamma, Y);
+  }
+
   // ---- NCCL ----------------------------------------------------------------------------------------------
   int comm_init(const void* id128, std::string& why) {
     if (g_.nranks == 1) return JFNK_OK;
@@ -465,6 +516,8 @@ class CudaOps : public DeviceOps {
   double* pinned_ = nullptr;
   ReduceWs ws_ = {nullptr, nullptr};
   double* halo_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::map<const void*, int> occupancy_;
+  double *dctx_ = nullptr, *dcty_ = nullptr; // orthonormal DCT-II matrices (nx x nx, ny x ny), built on first use
   SHParams shp_;
   int64_t launches_ = 0;
   bool profiling_ = false;

@@ -131,6 +131,20 @@ class DeviceOps {
   // F = (u - uval) - dt (F2 + Fprev)/2 ; norms as sh_residual
   virtual void droplet_combine(const DropletParams& dp, const double* u, const double* uval, const double* F2,
                                const double* Fprev, double* F, int norm_off) = 0;
+
+  // ---- moving-mesh relaxation (loop_pma / solve_PMA; PMA2_nk.py:345-403, droplet.py:578-599,729-760) ------
+  // out = monitor(u, lap): mode 0 |lap|^2, mode 1 1/(1+u)^6
+  virtual void pma_monitor(int mode, const double* u, const double* lap, double* out) = 0;
+  // one pass of the 9-point (edges 6-point, corners 4-point) smoothing filter
+  virtual void pma_smooth(const MeshParams& mp, const double* in, double* out) = 0;
+  // S[out_off] = sum mon |J|
+  virtual void pma_wsum(const double* mon, const double* J, int out_off) = 0;
+  // out = sqrt((mon + add) |J|) / alpha
+  virtual void pma_rhs(const double* mon, const double* J, ScalarRef add, double alpha, double* out) = 0;
+  // 2-D orthonormal DCT-II of the ny x nx field (inverse != 0: the inverse transform); tmp is scratch
+  virtual void pma_dct2(const double* in, double* tmp, double* out, int inverse) = 0;
+  // Y /= (1 - gamma Leig)
+  virtual void pma_spectral_divide(const MeshParams& mp, double gamma, double* Y) = 0;
 };
 
 } // namespace jfnk

@@ -202,6 +202,35 @@ int Engine::droplet_set_prev(const double* uval, double dt) {
   return ops_->status();
 }
 
+// loop_pma (droplet.py:590-599) / the single solve_PMA + explicit Euler update of PMA2_nk.py:94,103, on the device.
+// Every pass: metrics of the current Q, Laplacian of the (old) solution, monitor + smoothing + Mackenzie
+// regularisation, spectral solve, Q += dt Q_t.  (The script skips the derivative refresh in its first pass because
+// they are still current from the start of the step; recomputing them gives the same values.)
+int Engine::mesh_relax(double* Q, const double* Uval, double dt, int loops, const PmaParams& pp) {
+  if (!mesh_ready_) return fail(JFNK_INVALID, "jfnk_mesh_relax: call jfnk_mesh_setup first");
+  if (loops < 1) return fail(JFNK_INVALID, "jfnk_mesh_relax: loops must be >= 1");
+  if (!(pp.alpha > 0) || pp.smoothing_iters < 0 || pp.monitor_mode < 0 || pp.monitor_mode > 1)
+    return fail(JFNK_INVALID, "jfnk_mesh_relax: bad parameters");
+  const int deriv_bc = (cfg_.problem == JFNK_PROBLEM_DROPLET) ? 1 : 0;
+  const double cell = mp_.dksi * mp_.deta;
+  double *lap = scratch_[0], *a = scratch_[1], *b = scratch_[2], *t = scratch_[3], *spec = scratch_[4];
+  for (int it = 0; it < loops; ++it) {
+    ops_->mesh_metrics(mp_, Q, MF_);
+    if (pp.monitor_mode == 0) ops_->mesh_laplace(mp_, MF_, Uval, lap, nullptr, 1, deriv_bc);
+    ops_->pma_monitor(pp.monitor_mode, Uval, lap, a);
+    for (int s = 0; s < pp.smoothing_iters; ++s) { ops_->pma_smooth(mp_, a, b); std::swap(a, b); }
+    ops_->pma_wsum(a, MF_[3], JS_TMP0);
+    ops_->pma_rhs(a, MF_[3], sref(pp.cnorm * cell, JS_TMP0), pp.alpha, b); // sqrt((mon + C sum|J| dksi deta)|J|)/alpha
+    ops_->pma_dct2(b, t, spec, 0);
+    ops_->pma_spectral_divide(mp_, pp.gamma, spec);
+    ops_->pma_dct2(spec, t, b, 1);
+    ops_->lincomb(Q, sref(1.0), Q, sref(dt), b, -1);
+  }
+  metrics_ready_ = false; // Q moved on: the next step must call jfnk_mesh_set_potential (compute_Q_spatial_ders)
+  prev_ready_ = false;
+  return ops_->status();
+}
+
 bool Engine::problem_ready(std::string& why) const {
   switch (cfg_.problem) {
     case JFNK_PROBLEM_SH:

@@ -12,6 +12,7 @@
 #include <vector>
 #include "../../include/jfnk.h"
 #include "device_ops.h"
+#include "mesh_math.h"
 
 namespace jfnk {
 
@@ -51,6 +52,7 @@ class Engine {
   int pma2_set_prev(const double* uval);
   int droplet_setup(const DropletParams& dp);
   int droplet_set_prev(const double* uval, double dt);
+  int mesh_relax(double* Q, const double* Uval, double dt, int loops, const PmaParams& pp);
 
   // operator level
   int residual(const double* u, double* F);

@@ -228,4 +228,56 @@ JF_HD double droplet_combine_point(const DropletParams& p, double u, double uval
   return (u - uval) - p.dt * (F2 + Fprev) / 2.0;
 }
 
+
+// ---- moving-mesh relaxation (PMA): monitor function, smoothing filter, spectral solve -------------------
+// compute_and_smooth_monitor (PMA2_nk.py:345-391, droplet.py:729-760), solve_PMA (PMA2_nk.py:393-403,
+// droplet.py:578-588), loop_pma (droplet.py:590-599).
+struct PmaParams {
+  double alpha, gamma; // mesh adaption speed / extent of smoothing
+  double cnorm;        // Mackenzie regularisation constant (droplet C_ = 0.15; PMA2: 1)
+  int smoothing_iters; // 4
+  int monitor_mode;    // 0: |u_xx + u_yy|^2 ; 1: 1/(1+u)^6 (PMA2 with epsilon == 0)
+};
+
+JF_HD double pma_monitor_point(int mode, double u, double lap) {
+  if (mode == 1) { double q = 1.0 + u; double q2 = q * q; return 1.0 / (q2 * q2 * q2); }
+  double a = fabs(lap);
+  return a * a;
+}
+
+// one pass of the fourth-order filter (9-point interior, 6-point edges, 4-point corners)
+JF_HD double pma_smooth_point(const MeshGeom& g, const double* t, int r, int c) {
+  const int nx = g.nx, ny = g.ny;
+#define T_(rr, cc) t[(size_t)(rr) * nx + (cc)]
+  const bool top = (r == ny - 1), bot = (r == 0), lef = (c == 0), rig = (c == nx - 1);
+  if (!top && !bot && !lef && !rig)
+    return T_(r, c) + (T_(r - 1, c) + T_(r + 1, c) + T_(r, c - 1) + T_(r, c + 1)) / 8 +
+           (T_(r - 1, c - 1) + T_(r - 1, c + 1) + T_(r + 1, c - 1) + T_(r + 1, c + 1)) / 16;
+  if ((top || bot) && (lef || rig)) { // corners
+    int r1 = bot ? 1 : ny - 2, c1 = lef ? 1 : nx - 2;
+    return (4 * T_(r, c) + 2 * T_(r, c1) + 2 * T_(r1, c) + T_(r1, c1)) / 9;
+  }
+  if (lef || rig) { // vertical edges
+    int c1 = lef ? 1 : nx - 2;
+    return (4 * T_(r, c) + 2 * T_(r - 1, c) + 2 * T_(r + 1, c) + 2 * T_(r, c1) + T_(r + 1, c1) + T_(r - 1, c1)) / 12;
+  }
+  int r1 = bot ? 1 : ny - 2; // horizontal edges
+  return (4 * T_(r, c) + 2 * T_(r, c - 1) + 2 * T_(r, c + 1) + 2 * T_(r1, c) + T_(r1, c + 1) + T_(r1, c - 1)) / 12;
+#undef T_
+}
+
+// eigenvalues of the (DCT-diagonalised) discrete Laplacian used by the reference: M.Leig (droplet.py:831-833)
+JF_HD double pma_leig(const MeshGeom& g, int r, int c) {
+  const double pi = 3.141592653589793238462643383279502884;
+  return ((2 * cos(pi * r / (g.ny - 1)) - 2) + (2 * cos(pi * c / (g.nx - 1)) - 2)) / (g.dksi * g.deta);
+}
+
+// orthonormal DCT-II matrix entry C[k][n] of size N: s_k cos(pi (2n+1) k / (2N))  (scipy.fft.dct(norm="ortho"))
+JF_HD double dct2_entry(int k, int n, int N) {
+  const double pi = 3.141592653589793238462643383279502884;
+  long long m = ((long long)(2 * n + 1) * k) % (4LL * N); // exact argument reduction: period 4N
+  double cv = cos(pi * (double)m / (2.0 * N));
+  return (k == 0 ? sqrt(1.0 / N) : sqrt(2.0 / N)) * cv;
+}
+
 } // namespace jfnk

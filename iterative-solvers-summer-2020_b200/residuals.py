@@ -73,6 +73,20 @@ class _DeviceResidual:
     def _configure(self, ctx):  # push parameters / per-step state into a fresh context
         raise NotImplementedError
 
+    def profile(self, on=True):
+        """switch the per-kernel-class CUDA-event timing of the engine on / off"""
+        ctx = self.context()
+        ctx.check(ctx.lib.jfnk_profile_enable(ctx.handle, 1 if on else 0))
+
+    def profile_read(self):
+        """{class: {"launches", "ms", "bytes"}} since the last read (synchronises the stream)"""
+        ctx = self.context()
+        arr = (_capi.KernelStat * 32)()
+        cnt = C.c_int(0)
+        ctx.check(ctx.lib.jfnk_profile_read(ctx.handle, arr, 32, C.byref(cnt)))
+        return {arr[i].name.decode(): {"launches": int(arr[i].launches), "ms": float(arr[i].ms), "bytes": float(arr[i].bytes)}
+                for i in range(cnt.value)}
+
     # -- operator level ---------------------------------------------------------------------------
     def __call__(self, u):
         ctx = self.context()
@@ -175,20 +189,6 @@ class SHResidual(_DeviceResidual):
             ctx.check(rc, du if inplace else ctx.buf.to_user(du, U))
         return du if inplace else ctx.buf.to_user(du, U)
 
-    def profile(self, on=True):
-        """switch the per-kernel-class CUDA-event timing of the engine on / off"""
-        ctx = self.context()
-        ctx.check(ctx.lib.jfnk_profile_enable(ctx.handle, 1 if on else 0))
-
-    def profile_read(self):
-        """{class: {"launches", "ms", "bytes"}} since the last read (synchronises the stream)"""
-        ctx = self.context()
-        arr = (_capi.KernelStat * 32)()
-        cnt = C.c_int(0)
-        ctx.check(ctx.lib.jfnk_profile_read(ctx.handle, arr, 32, C.byref(cnt)))
-        return {arr[i].name.decode(): {"launches": int(arr[i].launches), "ms": float(arr[i].ms), "bytes": float(arr[i].bytes)}
-                for i in range(cnt.value)}
-
 
 class SHLinearised(_DeviceResidual):
     """Linearly-implicit Swift-Hohenberg stepper (sh_linearised.py:16-57): per step solve
@@ -247,6 +247,25 @@ class _MeshResidual(_DeviceResidual):
         ctx.check(ctx.lib.jfnk_mesh_set_potential(ctx.handle, ctx.buf.ptr(self._Q)))
         return self
 
+    # defaults of the PMA mesh relaxation, overridden per model
+    _pma_defaults = dict(alpha=0.1, gamma=0.1, cnorm=1.0, smoothing_iters=4, monitor_mode=0)
+
+    def relax_mesh(self, Q, Uval, dt, loops=1, **kw):
+        """Moving-mesh relaxation on the device: ``loops`` passes of the body of ``loop_pma`` (droplet.py:590-599),
+        i.e. ``solve_PMA(); Q.val += dt*Q.dt`` with the derivatives refreshed every pass; ``loops=1`` is the single
+        mesh update of PMA2_nk.py:94,103.  ``Uval`` is the OLD solution.  Returns the new ``Q`` (like ``Q``)."""
+        p = dict(self._pma_defaults)
+        p.update(kw)
+        ctx = self.context()
+        dQ = ctx.vec(Q, "Q")
+        dU = ctx.vec(Uval, "U.val")
+        ctx.check(ctx.lib.jfnk_mesh_relax(ctx.handle, ctx.buf.ptr(dQ), ctx.buf.ptr(dU), float(dt), int(loops),
+                                          float(p["alpha"]), float(p["gamma"]), float(p["cnorm"]),
+                                          int(p["smoothing_iters"]), int(p["monitor_mode"])))
+        self._Q = None  # the engine's metric fields are stale until set_mesh(Q) is called again
+        self._prev = None
+        return ctx.buf.to_user(dQ, Q)
+
     def laplace(self, v):
         """(v_xx, v_yy) = Laplace_operator(v, D_ksi v, D_eta v)."""
         ctx = self.context()
@@ -264,6 +283,9 @@ class PMA2Residual(_MeshResidual):
     """
 
     problem = _capi.PROBLEM_PMA2
+    # PMA2_nk.py:27-31 (alpha_, gamma_, smoothing_iters_); epsilon_ == 0 -> monitor 1/(1+u)**6 (:361-362);
+    # mon += mon_integral (:389-390)
+    _pma_defaults = dict(alpha=0.1, gamma=0.1, cnorm=1.0, smoothing_iters=4, monitor_mode=1)
 
     def __init__(self, N=51, *, lambd=1.0, beta=0.15, epsilon=0.0, m=3, dt=1e-4, endl=-1.0, endr=1.0, **kw):
         dksi = (endr - endl) / (N - 1)
@@ -288,6 +310,8 @@ class DropletResidual(_MeshResidual):
     """Residual of droplet.py:435-450 on the Nx x Ny moving mesh (defaults: droplet.py:23-53)."""
 
     problem = _capi.PROBLEM_DROPLET
+    # droplet.py:41-44 (alpha_, gamma_, C_), :31 (smoothing_iters_); monitor abs(u_xx + u_yy)**2 (:736)
+    _pma_defaults = dict(alpha=0.01, gamma=0.1, cnorm=0.15, smoothing_iters=4, monitor_mode=0)
 
     def __init__(self, Nx=91, Ny=61, *, endl=-3.0, endr=6.0, endb=-3.0, endt=3.0, epsilon=1e-2, n=6, m=3, Bo=0.01,
                  alpha2=0.0, epsilon2=None, **kw):

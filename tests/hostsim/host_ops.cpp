@@ -324,7 +324,56 @@ class HostOps : public DeviceOps {
     norms(F, u, norm_off);
   }
 
+  // ---- moving-mesh relaxation ------------------------------------------------------------------------
+  void pma_monitor(int mode, const double* u, const double* lap, double* out) override {
+    launches_++;
+    for (size_t e = 0; e < g_.n(); ++e) out[e] = pma_monitor_point(mode, u[e], mode == 1 ? 0.0 : lap[e]);
+  }
+  void pma_smooth(const MeshParams& mp, const double* in, double* out) override {
+    launches_++;
+    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    for (int r = 0; r < g_.ny; ++r)
+      for (int c = 0; c < g_.nx; ++c) out[(size_t)r * g_.nx + c] = pma_smooth_point(gm, in, r, c);
+  }
+  void pma_wsum(const double* mon, const double* J, int out_off) override {
+    launches_++;
+    double acc = 0;
+    for (size_t e = 0; e < g_.n(); ++e) acc += mon[e] * fabs(J[e]);
+    S_[out_off] = acc;
+  }
+  void pma_rhs(const double* mon, const double* J, ScalarRef add, double alpha, double* out) override {
+    launches_++;
+    double av = eval_sref(S_.data(), add);
+    for (size_t e = 0; e < g_.n(); ++e) out[e] = sqrt((mon[e] + av) * fabs(J[e])) / alpha;
+  }
+  static void gemm(int M, int N, int K, const double* A, int ta, const double* B, int tb, double* C) {
+    for (int i = 0; i < M; ++i)
+      for (int j = 0; j < N; ++j) {
+        double acc = 0;
+        for (int k = 0; k < K; ++k) acc += (ta ? A[(size_t)k * M + i] : A[(size_t)i * K + k]) * (tb ? B[(size_t)j * K + k] : B[(size_t)k * N + j]);
+        C[(size_t)i * N + j] = acc;
+      }
+  }
+  void pma_dct2(const double* in, double* tmp, double* out, int inverse) override {
+    launches_++;
+    const int nx = g_.nx, ny = g_.ny;
+    if (dctx_.empty()) {
+      dctx_.resize((size_t)nx * nx); dcty_.resize((size_t)ny * ny);
+      for (int k = 0; k < nx; ++k) for (int j = 0; j < nx; ++j) dctx_[(size_t)k * nx + j] = dct2_entry(k, j, nx);
+      for (int k = 0; k < ny; ++k) for (int j = 0; j < ny; ++j) dcty_[(size_t)k * ny + j] = dct2_entry(k, j, ny);
+    }
+    if (!inverse) { gemm(ny, nx, ny, dcty_.data(), 0, in, 0, tmp); gemm(ny, nx, nx, tmp, 0, dctx_.data(), 1, out); }
+    else { gemm(ny, nx, ny, dcty_.data(), 1, in, 0, tmp); gemm(ny, nx, nx, tmp, 0, dctx_.data(), 0, out); }
+  }
+  void pma_spectral_divide(const MeshParams& mp, double gamma, double* Y) override {
+    launches_++;
+    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    for (int r = 0; r < g_.ny; ++r)
+      for (int c = 0; c < g_.nx; ++c) { size_t e = (size_t)r * g_.nx + c; Y[e] = Y[e] / (1.0 - gamma * pma_leig(gm, r, c)); }
+  }
+
   void set_comm(hostsim_allreduce_fn ar, hostsim_halo_fn halo, void* user) { ar_ = ar; halo_ = halo; user_ = user; }
+  std::vector<double> dctx_, dcty_;
 
  private:
   Grid g_;

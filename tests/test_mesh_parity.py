@@ -84,6 +84,54 @@ def test_droplet_coalescence_steps_vs_reference_golden(buffers):
         U = Unew
 
 
+def test_mesh_relaxation_matches_loop_pma_and_solve_pma(buffers):
+    """loop_pma / solve_PMA / compute_and_smooth_monitor on the engine (dense
+    orthonormal DCT-II products instead of scipy.fft) against the oracle's restatement of the reference loop."""
+    g = np.load(os.path.join(GOLD, "droplet_91x61.npz"))
+    o = DropletOracle()
+    o.set_mesh(g["state_Q"])
+    o.set_prev(g["state_U"], 1e-4)
+    o.loop_pma(3e-9, 25)
+    F = jf.DropletResidual(buffers=buffers)
+    Q = F.relax_mesh(g["state_Q"], g["state_U"], 3e-9, loops=25)
+    dq_ref = o.Q - g["state_Q"]
+    assert rel(Q - g["state_Q"], dq_ref) < 1e-11  # the increment itself, not just Q
+    # the golden of the reference's own two steps: Q after step 0 is loop_pma(3e-9, 400) applied to the state
+    Q400 = F.relax_mesh(g["state_Q"], g["state_U"], 3e-9, loops=400)
+    assert rel(Q400 - g["state_Q"], g["run_Q0"] - g["state_Q"]) < 1e-10
+    # PMA2: one solve_PMA + explicit update (PMA2_nk.py:94,103) with the epsilon = 0 monitor 1/(1+u)^6
+    p = np.load(os.path.join(GOLD, "pma2_n51.npz"))
+    po = PMA2Oracle(N=51)
+    po.set_mesh(p["op_Q"])
+    po.Uval = p["op_Uval"].copy()
+    Qdt = po.ops.solve_pma(po.monitor(), po.met["J"], po.alpha, po.gamma)
+    P = jf.PMA2Residual(N=51, buffers=buffers)
+    Q2 = P.relax_mesh(p["op_Q"], p["op_Uval"], 1e-4, loops=1)
+    assert rel(Q2 - p["op_Q"], 1e-4 * Qdt) < 1e-12
+    with pytest.raises(ValueError):
+        P(p["op_u"])  # metric fields are stale after a relaxation: set_mesh must be called again
+
+
+def test_pma2_full_loop_on_engine_vs_reference_golden(buffers):
+    """PMA2_nk.py main() loop (:80-106) entirely on the engine: metrics, CN term, Newton-Krylov, mesh update."""
+    g = np.load(os.path.join(GOLD, "pma2_n51.npz"))
+    N, k = 51, 1e-4
+    F = jf.PMA2Residual(N=N, buffers=buffers)
+    xi = np.linspace(-1, 1, N)
+    X, Y = np.meshgrid(xi, xi)
+    Q = np.reshape(0.5 * X ** 2 + 0.5 * Y ** 2, N * N)
+    U = np.zeros(N * N)
+    for s in range(3):
+        F.set_mesh(Q)
+        F.set_prev(U)
+        dt = min((1 + U) ** 3) * k  # compute_g() * k (:91, :446-450)
+        Unew = jf.newton_krylov(F, U, verbose=0)
+        Q = F.relax_mesh(Q, U, dt, loops=1)  # solve_PMA() with the OLD solution; Q.val += dt * Q.dt (:94,:103)
+        assert rel(Unew, g[f"run_U{s}"]) < 1e-8, s
+        assert rel(Q, g[f"run_Q{s}"]) < 1e-12, s
+        U = Unew
+
+
 def test_droplet_state_file_round_trip(tmp_path):
     g = np.load(os.path.join(GOLD, "droplet_91x61.npz"))
     p = tmp_path / "initdrop_test.txt"
