@@ -88,10 +88,12 @@ def cpu_reference_sample(n_sample, steps, warmup):
     hist = []
     for _ in range(warmup):
         U = o.step(U)
-    t0 = time.perf_counter()
+    t0, c0 = time.perf_counter(), time.process_time()
     for _ in range(steps):
         U = o.step(U, history=hist)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
+    wall = time.perf_counter() - t0
+    cpu_reference_sample.effective_cores = round((time.process_time() - c0) / wall, 2)  # threads actually busy
+    dt = wall / max(steps, 1)
     nfev = float(np.mean([h["nfev"] for h in hist])) if hist else 0.0
     return dt, nfev
 
@@ -121,7 +123,9 @@ def run_reference(args, full_n):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"swift-hohenberg {full_n}^2 periodic, h={H}, k=0.2, r=0.01, g=1 (CPU sample {ns}^2)"},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": host_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": host_threads(),
+                         "effective_cores": getattr(cpu_reference_sample, "effective_cores", None), "kind": "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -293,7 +297,8 @@ def main():
         dt, nfev_cpu = cpu_reference_sample(ns, 1, 0)
         scale = (N / ns) ** 2
         line["cpu_baseline"] = {
-            "value": 1.0 / (dt * scale), "unit": "steps/s", "cores": host_threads(), "kind": "port",
+            "value": 1.0 / (dt * scale), "unit": "steps/s", "cores": host_threads(),
+            "effective_cores": getattr(cpu_reference_sample, "effective_cores", None), "kind": "port",
             "sample": (f"oracle/sh.py (SciPy newton_krylov + CSR L@u, the reference's path) 1 step on {ns}^2, same h/k/r/g: "
                        f"{dt:.2f} s, {nfev_cpu:.0f} F evals; extrapolated linearly in grid points x{scale:.0f} to {N}^2")}
     print(json.dumps(line))
