@@ -215,7 +215,7 @@ int jfnk_multi_dot(jfnk_ctx* ctx, int nv, const double* dV, size_t stride, const
   if (nv < 0 || nv > JF_MAXV) return set_err(JFNK_INVALID, "jfnk_multi_dot: nv out of range");
   const double* V[JF_MAXV + 1];
   for (int i = 0; i < nv; ++i) V[i] = dV + stride * (size_t)i;
-  ctx->ops->mdot(nv, V, dw, JS_RD, 0, 0.0);
+  ctx->ops->mdot(nv, V, dw, JS_RD);
   ctx->ops->allreduce_sum(JS_RD, nv + 1);
   if (out_host) ctx->ops->read_scalars(JS_RD, nv + 1, out_host);
   return done(ctx, ctx->ops->status());

@@ -14,8 +14,7 @@ namespace jfnk {
 // (two 256-thread CTAs per SM: <= 128 registers, checked with -Xptxas -v; one CTA/SM starves the memory pipe)
 template <int NV, int U>
 __global__ void __launch_bounds__(256, 2) mdot_kernel(PtrList V, int nv, const double* __restrict__ w, size_t n,
-                                                      double* S, int out_off, int guard, double tau2, ReduceWs ws) {
-  if (guard && !gs_second_pass_taken(S, nv, tau2)) return; // grid-uniform
+                                                      double* S, int out_off, ReduceWs ws) {
   double acc[NV + 1];
 #pragma unroll
   for (int k = 0; k <= NV; ++k) acc[k] = 0.0;
@@ -63,8 +62,7 @@ __global__ void __launch_bounds__(256, 2) mdot_kernel(PtrList V, int nv, const d
 // scalar-load variant for vectors that are not 16-byte aligned / odd leading dimension
 template <int NV>
 __global__ void __launch_bounds__(256) mdot_scalar_kernel(PtrList V, int nv, const double* __restrict__ w, size_t n,
-                                                          double* S, int out_off, int guard, double tau2, ReduceWs ws) {
-  if (guard && !gs_second_pass_taken(S, nv, tau2)) return;
+                                                          double* S, int out_off, ReduceWs ws) {
   double acc[NV + 1];
 #pragma unroll
   for (int k = 0; k <= NV; ++k) acc[k] = 0.0;
@@ -88,8 +86,7 @@ __global__ void __launch_bounds__(256) mdot_scalar_kernel(PtrList V, int nv, con
 // issued back to back), U = double2 elements per thread per sweep.
 template <int MODE, int NV, int U>
 __global__ void __launch_bounds__(256, 2) maxpy_kernel(PtrList V, int nv, double* __restrict__ w, size_t n, double* S,
-                                                       int c_off, int n2_off, int guard, double tau2, ReduceWs ws) {
-  if (guard && !gs_second_pass_taken(S, nv, tau2)) return;
+                                                       int c_off, int n2_off, int fuse_j, ReduceWs ws) {
   __shared__ double c[JF_MAXV];
   if (threadIdx.x < JF_MAXV) {
     double cv = 0.0;
@@ -151,14 +148,15 @@ __global__ void __launch_bounds__(256, 2) maxpy_kernel(PtrList V, int nv, double
     w[n - 1] = tt;
     acc[0] = fma(tt, tt, acc[0]);
   }
-  grid_reduce<1>(acc, 0u, ws, S + n2_off);
+  const bool last = grid_reduce<1>(acc, 0u, ws, S + n2_off);
+  // single-GPU fusion: the finalising CTA's thread 0 (which just wrote the norm) does the Givens step of column j
+  if (MODE == 0 && fuse_j >= 0 && last && threadIdx.x == 0) hess_givens_step(S, fuse_j, 0, 0);
 }
 
 // scalar-load variant for operands that are not 16-byte aligned
 template <int MODE>
 __global__ void __launch_bounds__(256) maxpy_scalar_kernel(PtrList V, int nv, double* __restrict__ w, size_t n, double* S,
-                                                           int c_off, int n2_off, int guard, double tau2, ReduceWs ws) {
-  if (guard && !gs_second_pass_taken(S, nv, tau2)) return;
+                                                           int c_off, int n2_off, int fuse_j, ReduceWs ws) {
   __shared__ double c[JF_MAXV];
   __shared__ const double* vp[JF_MAXV];
   if (threadIdx.x < nv) {
@@ -176,7 +174,8 @@ __global__ void __launch_bounds__(256) maxpy_scalar_kernel(PtrList V, int nv, do
     w[i] = t;
     acc[0] = fma(t, t, acc[0]);
   }
-  grid_reduce<1>(acc, 0u, ws, S + n2_off);
+  const bool last = grid_reduce<1>(acc, 0u, ws, S + n2_off);
+  if (MODE == 0 && fuse_j >= 0 && last && threadIdx.x == 0) hess_givens_step(S, fuse_j, 0, 0);
 }
 
 // out = a x + b y (y may be null), optional ||out||^2
@@ -227,7 +226,7 @@ __global__ void __launch_bounds__(256) maxabs_kernel(const double* v, size_t n, 
   grid_reduce<1>(acc, 1u, ws, S + out_off);
 }
 
-__global__ void givens_kernel(double* S, int j, int pass2, double tau2) { hess_givens_step(S, j, pass2, tau2); }
+__global__ void givens_kernel(double* S, int j, int taken, int rerun) { hess_givens_step(S, j, taken, rerun); }
 
 struct IdxList {
   int v[JF_MAXV];

@@ -43,7 +43,7 @@ __device__ __forceinline__ double warp_max(double v) {
 // block's partials, and let the LAST block to arrive reduce all partials in a fixed order and store the K
 // results to out[0..K).  Deterministic for a fixed grid.  Must be called by all threads of all blocks.
 template <int K>
-__device__ __forceinline__ void grid_reduce(double (&val)[K], unsigned maxmask, const ReduceWs& ws, double* out) {
+__device__ __forceinline__ bool grid_reduce(double (&val)[K], unsigned maxmask, const ReduceWs& ws, double* out) {
   __shared__ double sm[32][K];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
@@ -83,6 +83,7 @@ __device__ __forceinline__ void grid_reduce(double (&val)[K], unsigned maxmask, 
     }
     if (threadIdx.x == 0) *ws.ticket = 0u;
   }
+  return is_last; // true in every thread of the CTA that finalised (its thread 0 wrote out[0])
 }
 
 // multi-dot variant: val[0..nv) are dot accumulators (nv <= KMAX-1 at run time), val[KMAX-1] is w.w.

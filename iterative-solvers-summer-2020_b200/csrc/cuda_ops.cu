@@ -160,73 +160,71 @@ class CudaOps : public DeviceOps {
   }
 
   template <int NV>
-  void mdot_launch(bool vec, const PtrList& L, int nv, const double* w, int out_off, int guard, double tau2) {
+  void mdot_launch(bool vec, const PtrList& L, int nv, const double* w, int out_off) {
     size_t n = g_.n();
     constexpr int U = NV <= 4 ? 4 : (NV <= 8 ? 2 : 1);
-    Prof prof(this, guard ? K_MDOT2 : K_MDOT, nb(nv + 1)); // pass-2 launches may early-exit on device
-    if (vec) mdot_kernel<NV, U><<<resident_grid(mdot_kernel<NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, guard, tau2, ws_);
-    else mdot_scalar_kernel<NV><<<resident_grid(mdot_scalar_kernel<NV>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, guard, tau2, ws_);
+    Prof prof(this, out_off == JS_RD2 ? K_MDOT2 : K_MDOT, nb(nv + 1));
+    if (vec) mdot_kernel<NV, U><<<resident_grid(mdot_kernel<NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, ws_);
+    else mdot_scalar_kernel<NV><<<resident_grid(mdot_scalar_kernel<NV>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, ws_);
   }
-  void mdot(int nv, const double* const* V, const double* w, int out_off, int guard, double tau2) override {
+  void mdot(int nv, const double* const* V, const double* w, int out_off) override {
     if (nv > 32) {
       // more than 32 accumulators per thread would drop to one CTA per SM: two passes of <= 24 vectors instead
       // (w is read twice: +1 of nv+1 vectors).  The first pass parks w.w at out[h]; the second overwrites it.
       int h = nv / 2;
-      mdot(h, V, w, out_off, guard, tau2);
-      mdot_part(nv - h, nv, V + h, w, out_off + h, guard, tau2);
+      mdot(h, V, w, out_off);
+      mdot_part(nv - h, V + h, w, out_off + h);
       return;
     }
-    mdot_part(nv, nv, V, w, out_off, guard, tau2);
+    mdot_part(nv, V, w, out_off);
   }
-  // nv_guard: the vector count the device-side second-pass predicate refers to (RD[nv_guard] = w.w of pass 1)
-  void mdot_part(int nv, int nv_guard, const double* const* V, const double* w, int out_off, int guard, double tau2) {
-    (void)nv_guard;
+  void mdot_part(int nv, const double* const* V, const double* w, int out_off) {
     PtrList L;
     bool vec = aligned16(w);
     for (int i = 0; i < nv; ++i) { L.p[i] = V[i]; vec = vec && aligned16(V[i]); }
     for (int i = nv; i < JF_MAXV; ++i) L.p[i] = nullptr;
-    if (nv <= 2) mdot_launch<2>(vec, L, nv, w, out_off, guard, tau2);
-    else if (nv <= 4) mdot_launch<4>(vec, L, nv, w, out_off, guard, tau2);
-    else if (nv <= 8) mdot_launch<8>(vec, L, nv, w, out_off, guard, tau2);
-    else if (nv <= 12) mdot_launch<12>(vec, L, nv, w, out_off, guard, tau2);
-    else if (nv <= 16) mdot_launch<16>(vec, L, nv, w, out_off, guard, tau2);
-    else if (nv <= 20) mdot_launch<20>(vec, L, nv, w, out_off, guard, tau2);
-    else if (nv <= 24) mdot_launch<24>(vec, L, nv, w, out_off, guard, tau2);
-    else if (nv <= 28) mdot_launch<28>(vec, L, nv, w, out_off, guard, tau2);
-    else mdot_launch<32>(vec, L, nv, w, out_off, guard, tau2);
+    if (nv <= 2) mdot_launch<2>(vec, L, nv, w, out_off);
+    else if (nv <= 4) mdot_launch<4>(vec, L, nv, w, out_off);
+    else if (nv <= 8) mdot_launch<8>(vec, L, nv, w, out_off);
+    else if (nv <= 12) mdot_launch<12>(vec, L, nv, w, out_off);
+    else if (nv <= 16) mdot_launch<16>(vec, L, nv, w, out_off);
+    else if (nv <= 20) mdot_launch<20>(vec, L, nv, w, out_off);
+    else if (nv <= 24) mdot_launch<24>(vec, L, nv, w, out_off);
+    else if (nv <= 28) mdot_launch<28>(vec, L, nv, w, out_off);
+    else mdot_launch<32>(vec, L, nv, w, out_off);
   }
 
   template <int MODE>
-  void maxpy_launch(int nv, const double* const* V, double* w, int c_off, int n2_off, int guard, double tau2) {
+  void maxpy_launch(int nv, const double* const* V, double* w, int c_off, int n2_off, int fuse_j) {
     PtrList L;
     bool vec = aligned16(w);
     for (int i = 0; i < nv; ++i) { L.p[i] = V[i]; vec = vec && aligned16(V[i]); }
     for (int i = nv; i < JF_MAXV; ++i) L.p[i] = nullptr;
     size_t n = g_.n();
-    Prof prof(this, MODE == 2 ? K_MAXPY : (guard ? K_GS_UPDATE2 : K_GS_UPDATE), nb(MODE == 2 ? nv + 1 : nv + 2));
+    Prof prof(this, MODE == 2 ? K_MAXPY : (c_off == JS_RD2 ? K_GS_UPDATE2 : K_GS_UPDATE), nb(MODE == 2 ? nv + 1 : nv + 2));
     if (!vec) {
-      maxpy_scalar_kernel<MODE><<<resident_grid(maxpy_scalar_kernel<MODE>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, guard, tau2, ws_);
-    } else if (nv <= 4) maxpy_vec<MODE, 4, 4>(L, nv, w, c_off, n2_off, guard, tau2);
-    else if (nv <= 8) maxpy_vec<MODE, 8, 2>(L, nv, w, c_off, n2_off, guard, tau2);
-    else if (nv <= 16) maxpy_vec<MODE, 16, 1>(L, nv, w, c_off, n2_off, guard, tau2);
-    else if (nv <= 24) maxpy_vec<MODE, 24, 1>(L, nv, w, c_off, n2_off, guard, tau2);
-    else if (nv <= 32) maxpy_vec<MODE, 32, 1>(L, nv, w, c_off, n2_off, guard, tau2);
-    else maxpy_vec<MODE, JF_MAXV, 1>(L, nv, w, c_off, n2_off, guard, tau2);
+      maxpy_scalar_kernel<MODE><<<resident_grid(maxpy_scalar_kernel<MODE>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, fuse_j, ws_);
+    } else if (nv <= 4) maxpy_vec<MODE, 4, 4>(L, nv, w, c_off, n2_off, fuse_j);
+    else if (nv <= 8) maxpy_vec<MODE, 8, 2>(L, nv, w, c_off, n2_off, fuse_j);
+    else if (nv <= 16) maxpy_vec<MODE, 16, 1>(L, nv, w, c_off, n2_off, fuse_j);
+    else if (nv <= 24) maxpy_vec<MODE, 24, 1>(L, nv, w, c_off, n2_off, fuse_j);
+    else if (nv <= 32) maxpy_vec<MODE, 32, 1>(L, nv, w, c_off, n2_off, fuse_j);
+    else maxpy_vec<MODE, JF_MAXV, 1>(L, nv, w, c_off, n2_off, fuse_j);
   }
   // few vectors -> several elements per thread, so that every thread keeps >= 8 independent loads in flight
   template <int MODE, int NV, int U>
-  void maxpy_vec(const PtrList& L, int nv, double* w, int c_off, int n2_off, int guard, double tau2) {
+  void maxpy_vec(const PtrList& L, int nv, double* w, int c_off, int n2_off, int fuse_j) {
     size_t n = g_.n();
-    maxpy_kernel<MODE, NV, U><<<resident_grid(maxpy_kernel<MODE, NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, guard, tau2, ws_);
+    maxpy_kernel<MODE, NV, U><<<resident_grid(maxpy_kernel<MODE, NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, fuse_j, ws_);
   }
-  void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int guard, double tau2) override {
-    maxpy_launch<0>(nv, V, w, rd_off, n2_off, guard, tau2);
+  void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int fuse_givens_j) override {
+    maxpy_launch<0>(nv, V, w, rd_off, n2_off, g_.nranks == 1 ? fuse_givens_j : -1);
   }
   void maxpy_sub(int nv, const double* const* V, double* w, int n2_off) override {
-    maxpy_launch<1>(nv, V, w, JS_COEF, n2_off, 0, 0.0);
+    maxpy_launch<1>(nv, V, w, JS_COEF, n2_off, -1);
   }
   void maxpy(int nz, const double* const* Z, double* out, int n2_off) override {
-    maxpy_launch<2>(nz, Z, out, JS_COEF, n2_off, 0, 0.0);
+    maxpy_launch<2>(nz, Z, out, JS_COEF, n2_off, -1);
   }
   void lincomb(double* out, ScalarRef a, const double* x, ScalarRef b, const double* y, int n2_off) override {
     size_t n = g_.n();
@@ -250,9 +248,9 @@ class CudaOps : public DeviceOps {
     Prof prof(this, K_LINCOMB, nb(1));
     maxabs_kernel<<<stream_grid(n, 256), 256, 0, stream_>>>(v, n, S_, out_off, ws_);
   }
-  void givens(int j, int pass2, double tau2) override {
+  void givens(int j, int taken, int rerun) override {
     Prof prof(this, K_SCALAR, 0.0);
-    givens_kernel<<<1, 1, 0, stream_>>>(S_, j, pass2, tau2);
+    givens_kernel<<<1, 1, 0, stream_>>>(S_, j, taken, rerun);
   }
   void lsq(int nit, const int* zn2_idx, int scale_n2_idx) override {
     IdxList L;

@@ -72,10 +72,12 @@ class DeviceOps {
   virtual void allreduce_max(int off, int cnt) = 0;
 
   // ---- BLAS-1 on slab-local vectors of length grid.n() -------------------------------------------
-  // out[i] = V_i . w (i < nv), out[nv] = w . w.   guard != 0: skip unless gs_second_pass_taken(S, nv, tau2).
-  virtual void mdot(int nv, const double* const* V, const double* w, int out_off, int guard, double tau2) = 0;
-  // w -= sum_i (S[rd_off+i] / S[JS_VN2+i]) V_i ; S[n2_off] = ||w||^2.  guard as above.
-  virtual void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int guard, double tau2) = 0;
+  // out[i] = V_i . w (i < nv), out[nv] = w . w
+  virtual void mdot(int nv, const double* const* V, const double* w, int out_off) = 0;
+  // w -= sum_i (S[rd_off+i] / S[JS_VN2+i]) V_i ; S[n2_off] = ||w||^2.
+  // fuse_givens_j >= 0 (single rank only): the kernel's last CTA also performs the Hessenberg/Givens step of
+  // column j (first pass, not a re-run) right after finalising the norm -- one launch less per Arnoldi step.
+  virtual void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int fuse_givens_j) = 0;
   // w -= sum_i S[JS_COEF+i] V_i ; S[n2_off] = ||w||^2   (public microbenchmark form)
   virtual void maxpy_sub(int nv, const double* const* V, double* w, int n2_off) = 0;
   // out = sum_i S[JS_COEF+i] Z_i ; S[n2_off] = ||out||^2
@@ -87,7 +89,7 @@ class DeviceOps {
   virtual void copy(double* dst, const double* src) = 0;
   virtual void maxabs(const double* v, int out_off) = 0;
   // Hessenberg column + Givens update of Arnoldi step j; LSQ back-substitution (hd_math.h).
-  virtual void givens(int j, int pass2, double tau2) = 0;
+  virtual void givens(int j, int taken, int rerun) = 0;
   virtual void lsq(int nit, const int* zn2_idx, int scale_n2_idx) = 0;
 
   // ---- Swift-Hohenberg stencil operators --------------------------------------------------------

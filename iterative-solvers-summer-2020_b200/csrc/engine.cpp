@@ -345,7 +345,7 @@ int Engine::jvp(const double* v, double* Jv) {
   }
   if (!x0_) return fail(JFNK_INVALID, "jfnk_jvp: call jfnk_linearize first");
   // ||v||^2 -> TMP1 ; the operator divides by ||v||, scale back by ||v|| afterwards (0*v when ||v|| == 0)
-  ops_->mdot(0, nullptr, v, JS_TMP1, 0, 0.0);
+  ops_->mdot(0, nullptr, v, JS_TMP1);
   ops_->allreduce_sum(JS_TMP1, 1);
   double vn2;
   ops_->read_scalars(JS_TMP1, 1, &vn2);
@@ -373,9 +373,8 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
   int znidx[JF_MAXV];
   vs[0] = v0vec;
   ops_->write_scalars(JS_VN2 + 0, 1, &v0n2);
-  const int pass2 = (cfg_.gs_mode != JFNK_GS_CGS);
-  const double tau2 = (cfg_.gs_mode == JFNK_GS_CGS2) ? std::numeric_limits<double>::infinity()
-                                                      : cfg_.gs_tau * cfg_.gs_tau;
+  const double tau2 = cfg_.gs_tau * cfg_.gs_tau;
+  const bool single = (grid_.nranks == 1);
   int nit = 0;
   double res = NAN;
   for (int j = 0; j < m; ++j) {
@@ -389,27 +388,44 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
     double* w = VS_[j];
     vs[j + 1] = w;
     apply_operator(z, zi, w, true);
-    // classical Gram-Schmidt against vs[0..j]: all dots in one fused reduction, then one fused update
-    ops_->mdot(j + 1, vs, w, JS_RD, 0, 0.0);
+    // classical Gram-Schmidt against vs[0..j]: all dots in one fused reduction, then one fused update.
+    // One host round-trip per Arnoldi step: {w.w, ||w||^2 after pass 1, residual estimate, flags}.  The host
+    // decides from it whether a second (re-orthogonalisation) pass is needed; only then more work is enqueued.
+    ops_->mdot(j + 1, vs, w, JS_RD);
     ops_->allreduce_sum(JS_RD, j + 2);
-    ops_->gs_update(j + 1, vs, w, JS_RD, JS_HN2A, 0, 0.0);
-    ops_->allreduce_sum(JS_HN2A, 1);
-    if (pass2) {
-      ops_->mdot(j + 1, vs, w, JS_RD2, 1, tau2);
+    bool second = (cfg_.gs_mode == JFNK_GS_CGS2);
+    double sc[5]; // JS_WW, JS_HN2A, JS_HN2B, JS_RES, JS_FLAGS
+    if (!second) {
+      ops_->gs_update(j + 1, vs, w, JS_RD, JS_HN2A, single ? j : -1); // single GPU: Givens fused into the last CTA
+      ops_->allreduce_sum(JS_HN2A, 1);
+      if (!single) ops_->givens(j, 0, 0);
+      ops_->read_scalars(JS_WW, 5, sc);
+      second = (cfg_.gs_mode == JFNK_GS_CGS_IFNEEDED) && (sc[1] < tau2 * sc[0]);
+      if (second) {
+        ops_->mdot(j + 1, vs, w, JS_RD2);
+        ops_->allreduce_sum(JS_RD2, j + 1);
+        ops_->gs_update(j + 1, vs, w, JS_RD2, JS_HN2B, -1);
+        ops_->allreduce_sum(JS_HN2B, 1);
+        ops_->givens(j, 1, 1); // redo column j with h = (RD + RD2)/||V||, ||w|| from pass 2
+        ops_->read_scalars(JS_WW, 5, sc);
+      }
+    } else {
+      ops_->gs_update(j + 1, vs, w, JS_RD, JS_HN2A, -1);
+      ops_->allreduce_sum(JS_HN2A, 1);
+      ops_->mdot(j + 1, vs, w, JS_RD2);
       ops_->allreduce_sum(JS_RD2, j + 1);
-      ops_->gs_update(j + 1, vs, w, JS_RD2, JS_HN2B, 1, tau2);
+      ops_->gs_update(j + 1, vs, w, JS_RD2, JS_HN2B, -1);
       ops_->allreduce_sum(JS_HN2B, 1);
+      ops_->givens(j, 1, 0);
+      ops_->read_scalars(JS_WW, 5, sc);
     }
-    ops_->givens(j, pass2, tau2);
-    double rf[2];
-    ops_->read_scalars(JS_RES, 2, rf); // the one host round-trip of an Arnoldi step
     int st = ops_->status();
     if (st) return st;
-    res = rf[0];
-    int flags = (int)rf[1];
+    res = sc[3];
+    int flags = (int)sc[4];
     nit = j + 1;
     inner_total_++;
-    if (flags & JF_FLAG_REORTH) reorth_total_++;
+    if (second) reorth_total_++;
     if (flags & JF_FLAG_NONFINITE) return fail(JFNK_NONFINITE, "Function returned non-finite results");
     if (res < ptol || (flags & JF_FLAG_BREAKDOWN)) break;
   }
@@ -438,7 +454,7 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
 // scipy.sparse.linalg.lgmres with x0 = 0 (lgmres.py:124-232), general number of outer cycles.
 int Engine::lgmres_general(const double* b, double* x, double rtol, int maxiter, int* info, double* res_out,
                            int* inner_out) {
-  ops_->mdot(0, nullptr, b, JS_TMP0, 0, 0.0);
+  ops_->mdot(0, nullptr, b, JS_TMP0);
   ops_->allreduce_sum(JS_TMP0, 1);
   double bn2;
   ops_->read_scalars(JS_TMP0, 1, &bn2);
@@ -463,7 +479,7 @@ int Engine::lgmres_general(const double* b, double* x, double rtol, int maxiter,
     if (x_is_zero) { v0vec = b; v0n2 = bn2; r_norm = bnorm; }
     else {
       // r_outer = A x - b ; v0 = -r_outer
-      ops_->mdot(0, nullptr, x, JS_TMP1, 0, 0.0);
+      ops_->mdot(0, nullptr, x, JS_TMP1);
       ops_->allreduce_sum(JS_TMP1, 1);
       apply_operator(x, JS_TMP1, FT_, true);
       ops_->lincomb(FT_, sref(1.0), b, sref(-1.0, -1, JS_TMP1, -1), FT_, JS_TMP2);

@@ -68,13 +68,9 @@ JF_HD double shlin_apply(const SHParams& p, double z, double Lz, double D) { ret
 // Mirrors what qr_insert + |Q[0,-1]| compute in _fgmres (_gcrotmk.py:149-168) for the growing
 // Hessenberg matrix, in the standard GMRES form: rotations cs/sn, rotated rhs g (g[0]=1).
 // S = scalar arena.  j = Arnoldi index (column), so the column has j+2 entries.
-// pass2 != 0: the second Gram-Schmidt pass kernels were enqueued with threshold tau2; whether they
-// actually ran is the device-side predicate gs_second_pass_taken() that those kernels evaluate too.
-JF_HD bool gs_second_pass_taken(const double* S, int nv, double tau2) {
-  return S[JS_HN2A] < tau2 * S[JS_RD + nv];
-}
-
-JF_HD void hess_givens_step(double* S, int j, int pass2, double tau2) {
+// taken != 0: a second Gram-Schmidt pass was made (RD2, HN2B valid).  rerun != 0: the step for this j already ran
+// once after the first pass (the host then decided to re-orthogonalise): restart from the saved rotated rhs.
+JF_HD void hess_givens_step(double* S, int j, int taken, int rerun) {
   const double eps = 2.220446049250313e-16;
   double* rd = S + JS_RD;
   double* rd2 = S + JS_RD2;
@@ -86,10 +82,11 @@ JF_HD void hess_givens_step(double* S, int j, int pass2, double tau2) {
   int flags = 0;
   double ww = rd[j + 1];
   S[JS_WW] = ww;
-  bool taken = pass2 && gs_second_pass_taken(S, j + 1, tau2);
   double hn2 = taken ? S[JS_HN2B] : S[JS_HN2A];
   if (taken) flags |= JF_FLAG_REORTH;
   if (j == 0) g[0] = 1.0;
+  if (rerun) g[j] = S[JS_GJ_SAVE];
+  else S[JS_GJ_SAVE] = g[j];
   // h_i = (V_i . w)/||V_i|| with V_i stored unnormalised
   double hprev = 0.0;
   for (int i = 0; i <= j; ++i) {

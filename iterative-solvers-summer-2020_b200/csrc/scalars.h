@@ -22,7 +22,8 @@ enum ScalarSlot : int {
   JS_RES,  // |g_{j+1}|: GMRES residual estimate relative to ||v0|| = 1   -> host
   JS_FLAGS, // bit0 breakdown, bit1 non-finite, bit2 second GS pass taken -> host
   JS_DXN2, // ||dx||^2 of the assembled LGMRES correction
-  JS_pad2, JS_pad3,
+  JS_GJ_SAVE, // rotated rhs entry g[j] before the Givens step of column j (for a re-run after a second GS pass)
+  JS_pad3,
   JS_RD = 20,                 // [JF_MAXV+1] raw dots V_i.w ; RD[nv] = w.w
   JS_RD2 = JS_RD + JF_MAXV + 1, // [JF_MAXV+1] second-pass raw dots
   JS_VN2 = JS_RD2 + JF_MAXV + 1, // [JF_MAXV+1] squared norms of the (unnormalised) Arnoldi vectors

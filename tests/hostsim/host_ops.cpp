@@ -39,9 +39,8 @@ class HostOps : public DeviceOps {
   void allreduce_sum(int off, int cnt) override { if (g_.nranks > 1) ar_(user_, &S_[off], cnt, 0); }
   void allreduce_max(int off, int cnt) override { if (g_.nranks > 1) ar_(user_, &S_[off], cnt, 1); }
 
-  void mdot(int nv, const double* const* V, const double* w, int out_off, int guard, double tau2) override {
+  void mdot(int nv, const double* const* V, const double* w, int out_off) override {
     launches_++;
-    if (guard && !gs_second_pass_taken(S_.data(), nv, tau2)) return;
     size_t n = g_.n();
     for (int i = 0; i < nv; ++i) {
       double acc = 0;
@@ -52,9 +51,8 @@ class HostOps : public DeviceOps {
     for (size_t e = 0; e < n; ++e) acc += w[e] * w[e];
     S_[out_off + nv] = acc;
   }
-  void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int guard, double tau2) override {
+  void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int fuse_givens_j) override {
     launches_++;
-    if (guard && !gs_second_pass_taken(S_.data(), nv, tau2)) return;
     size_t n = g_.n();
     std::vector<double> c(nv);
     for (int i = 0; i < nv; ++i) c[i] = S_[rd_off + i] / S_[JS_VN2 + i];
@@ -66,6 +64,7 @@ class HostOps : public DeviceOps {
       acc += t * t;
     }
     S_[n2_off] = acc;
+    if (fuse_givens_j >= 0 && g_.nranks == 1) hess_givens_step(S_.data(), fuse_givens_j, 0, 0);
   }
   void maxpy_sub(int nv, const double* const* V, double* w, int n2_off) override {
     launches_++;
@@ -120,7 +119,7 @@ class HostOps : public DeviceOps {
     for (size_t e = 0; e < g_.n(); ++e) m = fmax(m, fabs(v[e]));
     S_[out_off] = m;
   }
-  void givens(int j, int pass2, double tau2) override { launches_++; hess_givens_step(S_.data(), j, pass2, tau2); }
+  void givens(int j, int taken, int rerun) override { launches_++; hess_givens_step(S_.data(), j, taken, rerun); }
   void lsq(int nit, const int* zn2_idx, int scale_n2_idx) override { launches_++; lsq_solve(S_.data(), nit, zn2_idx, scale_n2_idx); }
 
   // ---- Swift-Hohenberg ---------------------------------------------------------------------------

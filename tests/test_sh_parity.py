@@ -27,7 +27,7 @@ def relmax(a, b):
 CASES = [(61, 40.0), (64, 40.0)]  # config 1: the droplet-sized 61 and the script's N = 64
 
 
-@pytest.mark.parametrize("N,d", CASES + [(96, 60.0)])
+@pytest.mark.parametrize("N,d", CASES + [(96, 60.0), (5, 2.0)])  # (5, 2.0): the C++ driver's grid (main.cpp:3-4)
 def test_spmv_matches_reference_matrices(buffers, N, d):
     o = SHOracle(N=N, d=d)
     F = jf.SHResidual(N=N, d=d, buffers=buffers)
