@@ -149,8 +149,66 @@ JF_HD double v_eta_bc(const MeshGeom& g, const double* v, int r, int c, int deri
   return d_eta(g, v, r, c);
 }
 
+// Interior fast path of Laplace_operator: every stencil involved is the centred one (no closure rows/columns within
+// reach: 4 <= r < ny-4, 4 <= c < nx-4), so the formula is straight-line code with compile-time weights -- the same
+// arithmetic, in the same order, as the general path below.
+JF_HD void mesh_laplace_interior(const MeshGeom& g, const double* const* M, const double* v, int r, int c, double& vxx,
+                                 double& vyy) {
+  const size_t nx = g.nx;
+  const size_t e = (size_t)r * nx + c;
+  const double* A11 = M[4] + e;
+  const double* A22 = M[5] + e;
+  const double* A12 = M[6] + e;
+  const double* p = v + e;
+#define VX(k) p[(k)]
+#define VY(k) p[(ptrdiff_t)(k) * (ptrdiff_t)nx]
+#define AX(k) A11[(k)]
+#define AY(k) A22[(ptrdiff_t)(k) * (ptrdiff_t)nx]
+  double xx = (4 * (AX(-1) * (VX(-3) - 8 * VX(-2) + 8 * VX(0) - VX(1))) -
+               (-AX(-2) + 9 * AX(-1) + 9 * AX(0) - AX(1)) * (VX(-2) - 27 * VX(-1) + 27 * VX(0) - VX(1)) +
+               (-AX(-1) + 9 * AX(0) + 9 * AX(1) - AX(2)) * (VX(-1) - 27 * VX(0) + 27 * VX(1) - VX(2)) -
+               4 * (AX(1) * (VX(-1) - 8 * VX(0) + 8 * VX(2) - VX(3)))) /
+              (288 * g.dksi2);
+  double yy = (4 * (AY(-1) * (VY(-3) - 8 * VY(-2) + 8 * VY(0) - VY(1))) -
+               (-AY(-2) + 9 * AY(-1) + 9 * AY(0) - AY(1)) * (VY(-2) - 27 * VY(-1) + 27 * VY(0) - VY(1)) +
+               (-AY(-1) + 9 * AY(0) + 9 * AY(1) - AY(2)) * (VY(-1) - 27 * VY(0) + 27 * VY(1) - VY(2)) -
+               4 * (AY(1) * (VY(-1) - 8 * VY(0) + 8 * VY(2) - VY(3)))) /
+              (288 * g.deta2);
+#undef VX
+#undef VY
+#undef AX
+#undef AY
+  // centred first derivative weights (row type 2), columns / rows -2,-1,+1,+2 (the weight of 0 is 0)
+  const double* wx = g.d1x[2];
+  const double* wy = g.d1y[2];
+  const ptrdiff_t sx = (ptrdiff_t)nx;
+  // D_ksi(A12 * D_eta v): sum_k wx[k] * A12(r, c+k-2) * sum_a wy[a] v(r+a-2, c+k-2)
+  double accx = 0.0, accy = 0.0;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (k == 2) continue;
+    const double* q = p + (k - 2);
+    double ve = wy[0] * q[-2 * sx] + wy[1] * q[-sx] + wy[2] * q[0] + wy[3] * q[sx] + wy[4] * q[2 * sx];
+    accx += wx[k] * (A12[k - 2] * ve);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (k == 2) continue;
+    const double* q = p + (ptrdiff_t)(k - 2) * sx;
+    double vk = wx[0] * q[-2] + wx[1] * q[-1] + wx[2] * q[0] + wx[3] * q[1] + wx[4] * q[2];
+    accy += wy[k] * (A12[(ptrdiff_t)(k - 2) * sx] * vk);
+  }
+  const double Jv = M[3][e];
+  vxx = (xx + accx) / Jv;
+  vyy = (yy + accy) / Jv;
+}
+
 JF_HD void mesh_laplace_point(const MeshGeom& g, const double* const* M, const double* v, int r, int c, int deriv_bc,
                               double& vxx, double& vyy) {
+  if (r >= 4 && r < g.ny - 4 && c >= 4 && c < g.nx - 4) { // no closure stencil within reach
+    mesh_laplace_interior(g, M, v, r, c, vxx, vyy);
+    return;
+  }
   const double* J = M[3];
   const double* A11 = M[4];
   const double* A22 = M[5];

@@ -283,3 +283,18 @@ def test_argument_errors(buffers):
         jf.SHResidual(N=3, buffers=buffers).context()
     with pytest.raises(ValueError):
         F.jvp(np.ones(64 * 64))  # linearize not called
+
+
+def test_nonfinite_residual_raises_like_scipy(buffers):
+    """KrylovJacobian.matvec raises ValueError('Function returned non-finite results') (_nonlin.py:1563-1564)."""
+    N = 32
+    F = jf.SHResidual(N=N, d=20.0, buffers=buffers)
+    U0 = 1e120 * seeded_state(N, 9)  # u^3 overflows to inf
+    F.set_prev(U0)
+    with pytest.raises(ValueError):
+        jf.newton_krylov(F, U0, maxiter=5)
+    # the context stays usable afterwards
+    U1 = seeded_state(N, 9)
+    F.set_prev(U1)
+    out = jf.newton_krylov(F, U1)
+    assert np.isfinite(out).all()
