@@ -59,7 +59,8 @@ enum {
  * the device path batches all dots of one Arnoldi step into one reduction = classical GS). */
 enum {
   JFNK_GS_CGS = 0,          /* classical GS, one pass */
-  JFNK_GS_CGS_IFNEEDED = 1, /* second pass when ||w_after|| < gs_tau * ||w_before|| (decided on device) */
+  JFNK_GS_CGS_IFNEEDED = 1, /* second pass when ||w_after|| < gs_tau * ||w_before||; decided by the host from the
+                               scalars it reads back once per Arnoldi step anyway */
   JFNK_GS_CGS2 = 2          /* always two passes */
 };
 
@@ -74,9 +75,11 @@ typedef struct {
   int32_t inner_m;        /* LGMRES inner_m  (scipy default 30; lgmres.py:17) */
   int32_t outer_k;        /* LGMRES outer_k  (KrylovJacobian default 10; _nonlin.py:1477) */
   int32_t gs_mode;        /* JFNK_GS_* */
-  int32_t kernel_variant; /* 0 = marching shared-memory stencil kernels (product); 1 = one-thread-per-point
-                             cross-check kernels (same arithmetic, used by the parity tests) */
-  double gs_tau;          /* threshold for JFNK_GS_CGS_IFNEEDED (default 1/sqrt(2)) */
+  int32_t kernel_variant; /* Swift-Hohenberg stencil kernel selection: 0 = product rule (TMA-pipelined marching kernel
+                             for even grids >= 256 x 32, one-thread-per-point kernel otherwise); 1 = always the
+                             per-point kernel; 2 = the marching kernel wherever it is legal (even nx, 16-byte aligned
+                             fields).  1 and 2 exist so that the parity tests can cross-check the two kernels. */
+  double gs_tau;          /* threshold for JFNK_GS_CGS_IFNEEDED (Python default 0.25) */
   void* stream;           /* cudaStream_t; NULL = default stream */
 } jfnk_config;
 

@@ -126,7 +126,6 @@ class Context:
         rc = self.lib.jfnk_create(C.byref(cfg), self._ws_ptr, C.c_size_t(nbytes), C.byref(handle))
         raise_for_status(self.lib, rc)
         self.handle = handle
-        self._cb_keepalive = None
 
     def close(self):
         if getattr(self, "handle", None):

@@ -59,6 +59,7 @@ class CudaOps : public DeviceOps {
     for (auto& r : recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : free_events_) cudaEventDestroy(e);
     for (int i = 0; i < 6; ++i) if (halo_[i]) cudaFree(halo_[i]);
+    if (dtab_) cudaFree(dtab_);
     if (dctx_) cudaFree(dctx_);
     if (dcty_) cudaFree(dcty_);
     if (pinned_) cudaFreeHost(pinned_);
@@ -387,29 +388,46 @@ class CudaOps : public DeviceOps {
   }
 
   // ---- moving mesh -------------------------------------------------------------------------------------
+  // geometry + device-resident weight tables (re-uploaded only when the spacings change)
+  MeshGeom geom(const MeshParams& mp) {
+    if (!dtab_) ck(cudaMalloc(&dtab_, sizeof(MeshTables)), "cudaMalloc(mesh tables)");
+    if (!tab_valid_ || mp.dksi != last_mp_.dksi || mp.deta != last_mp_.deta) {
+      MeshTables t;
+      fill_mesh_tables(mp, t);
+      ck(cudaMemcpyAsync(dtab_, &t, sizeof(t), cudaMemcpyHostToDevice, stream_), "H2D mesh tables");
+      ck(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"); // `t` is a stack temporary
+      tab_valid_ = true;
+    }
+    last_mp_ = mp;
+    return make_geom(mp, g_.nx, g_.ny, dtab_);
+  }
+  // grid of the 32 x 8 tiled stencil kernels
+  int tile_grid() const {
+    long long t = (long long)((g_.nx + 31) / 32) * ((g_.ny + 7) / 8);
+    return (int)std::max<long long>(1, std::min<long long>(t, (long long)sms_ * 8));
+  }
   static MetricCPtrs cptrs(const double* const* M) {
     MetricCPtrs P;
     for (int i = 0; i < 7; ++i) P.m[i] = M[i];
     return P;
   }
   void mesh_metrics(const MeshParams& mp, const double* Q, double* const* M) override {
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     MetricPtrs P;
     for (int i = 0; i < 7; ++i) P.m[i] = M[i];
     Prof prof(this, K_MESH, nb(8));
-    mesh_metrics_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, Q, P);
+    mesh_metrics_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, Q, P);
   }
   void mesh_laplace(const MeshParams& mp, const double* const* M, const double* v, double* vxx, double* vyy,
                     int sum_only, int deriv_bc) override {
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     Prof prof(this, K_MESH, nb(sum_only ? 6 : 7));
-    mesh_laplace_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, cptrs(M), v, vxx, vyy, sum_only, deriv_bc);
+    mesh_laplace_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), v, vxx, vyy, sum_only, deriv_bc);
   }
   void pma2_rhs(const Pma2Params& pp, const double* u, const double* lap2, double* out) override {
-    MeshParams mp; memset(&mp, 0, sizeof(mp)); mp.dksi = mp.deta = 1.0;
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(last_mp_);
     Prof prof(this, K_MESH, nb(3));
-    pma2_rhs_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, pp, u, lap2, out);
+    pma2_rhs_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, pp, u, lap2, out);
   }
   void pma2_combine(const Pma2Params& pp, const double* u, const double* uval, const double* rhs, const double* cn,
                     double* F, int norm_off) override {
@@ -422,14 +440,14 @@ class CudaOps : public DeviceOps {
   }
   void droplet_flux(const MeshParams& mp, const DropletParams& dp, const double* const* M, const double* p,
                     const double* h, double* A, double* B) override {
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     Prof prof(this, K_MESH, nb(8));
-    droplet_flux_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, dp, cptrs(M), p, h, A, B);
+    droplet_flux_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, dp, cptrs(M), p, h, A, B);
   }
   void droplet_div(const MeshParams& mp, const double* const* M, const double* A, const double* B, double* out) override {
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     Prof prof(this, K_MESH, nb(7));
-    droplet_div_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, cptrs(M), A, B, out);
+    droplet_div_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), A, B, out);
   }
   void droplet_combine(const DropletParams& dp, const double* u, const double* uval, const double* F2,
                        const double* Fprev, double* F, int norm_off) override {
@@ -443,7 +461,7 @@ class CudaOps : public DeviceOps {
     pma_monitor_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(g_.n(), mode, u, lap, out);
   }
   void pma_smooth(const MeshParams& mp, const double* in, double* out) override {
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     Prof prof(this, K_MESH, nb(2));
     pma_smooth_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, in, out);
   }
@@ -478,7 +496,7 @@ class CudaOps : public DeviceOps {
     }
   }
   void pma_spectral_divide(const MeshParams& mp, double gamma, double* Y) override {
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     Prof prof(this, K_MESH, nb(2));
     pma_divide_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(gm, gamma, Y);
   }
@@ -515,6 +533,9 @@ class CudaOps : public DeviceOps {
   ReduceWs ws_ = {nullptr, nullptr};
   double* halo_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::map<const void*, int> occupancy_;
+  MeshTables* dtab_ = nullptr;
+  bool tab_valid_ = false;
+  MeshParams last_mp_ = {1.0, 1.0, 0, 0, 0, 0};
   double *dctx_ = nullptr, *dcty_ = nullptr; // orthonormal DCT-II matrices (nx x nx, ny x ny), built on first use
   SHParams shp_;
   int64_t launches_ = 0;

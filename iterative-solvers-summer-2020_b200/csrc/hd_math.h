@@ -8,8 +8,10 @@
 
 #if defined(__CUDACC__)
 #define JF_HD __host__ __device__ __forceinline__
+#define JF_UNROLL _Pragma("unroll")
 #else
 #define JF_HD inline
+#define JF_UNROLL
 #endif
 
 namespace jfnk {

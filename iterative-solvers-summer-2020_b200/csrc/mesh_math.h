@@ -12,12 +12,20 @@
 
 namespace jfnk {
 
+// 1-D finite-difference weight tables (row type x tap), already divided by 12h / 12h^2.  They live in device
+// (or, for the CPU test double, host) memory and are reached through a pointer: indexing a by-value kernel
+// parameter with a run-time row type would make every thread copy the whole struct to local memory.
+struct MeshTables {
+  double d1x[5 * 5], d1y[5 * 5]; // [row type][k]
+  double d2x[5 * 6], d2y[5 * 6];
+};
+
 struct MeshGeom {
   int nx, ny;
   double dksi, deta, dksi2, deta2;
   double bl, br, bb, bt;
-  double d1x[5][5], d1y[5][5]; // [row type][k] weights, already divided by 12h
-  double d2x[5][6], d2y[5][6]; // [row type][k] weights, already divided by 12h^2
+  double c1x[5], c1y[5]; // centred first-derivative weights (row type 2), by value for the interior fast path
+  const MeshTables* tab;
 };
 
 // row type of index i in a dimension of n points: 0,1 = first two rows, 3,4 = last two rows, 2 = interior
@@ -27,18 +35,26 @@ JF_HD int d1_start(int i, int n, int type) { return type < 2 ? 0 : (type > 2 ? n
 JF_HD int d2_start(int i, int n, int type) { return type < 2 ? 0 : (type > 2 ? n - 6 : i - 2); }
 JF_HD int d2_count(int type) { return type == 2 ? 5 : 6; }
 
-inline MeshGeom make_geom(const MeshParams& mp, int nx, int ny) {
+inline void fill_mesh_tables(const MeshParams& mp, MeshTables& t) {
+  const double dksi2 = mp.dksi * mp.dksi, deta2 = mp.deta * mp.deta;
+  const double c1[5][5] = {{-25, 48, -36, 16, -3}, {-3, -10, 18, -6, 1}, {1, -8, 0, 8, -1}, {-1, 6, -18, 10, 3}, {3, -16, 36, -48, 25}};
+  const double c2[5][6] = {{-415.0 / 6, 96, -36, 32.0 / 3, -1.5, 0}, {10, -15, -4, 14, -6, 1}, {-1, 16, -30, 16, -1, 0},
+                           {1, -6, 14, -4, -15, 10}, {0, -1.5, 32.0 / 3, -36, 96, -415.0 / 6}};
+  for (int r = 0; r < 5; ++r) {
+    for (int k = 0; k < 5; ++k) { t.d1x[r * 5 + k] = c1[r][k] / (12 * mp.dksi); t.d1y[r * 5 + k] = c1[r][k] / (12 * mp.deta); }
+    for (int k = 0; k < 6; ++k) { t.d2x[r * 6 + k] = c2[r][k] / (12 * dksi2); t.d2y[r * 6 + k] = c2[r][k] / (12 * deta2); }
+  }
+}
+
+// `tab` must point to tables filled for the same MeshParams, in memory the executing side can read
+inline MeshGeom make_geom(const MeshParams& mp, int nx, int ny, const MeshTables* tab) {
   MeshGeom g;
   g.nx = nx; g.ny = ny;
   g.dksi = mp.dksi; g.deta = mp.deta; g.dksi2 = mp.dksi * mp.dksi; g.deta2 = mp.deta * mp.deta;
   g.bl = mp.bl; g.br = mp.br; g.bb = mp.bb; g.bt = mp.bt;
-  const double c1[5][5] = {{-25, 48, -36, 16, -3}, {-3, -10, 18, -6, 1}, {1, -8, 0, 8, -1}, {-1, 6, -18, 10, 3}, {3, -16, 36, -48, 25}};
-  const double c2[5][6] = {{-415.0 / 6, 96, -36, 32.0 / 3, -1.5, 0}, {10, -15, -4, 14, -6, 1}, {-1, 16, -30, 16, -1, 0},
-                           {1, -6, 14, -4, -15, 10}, {0, -1.5, 32.0 / 3, -36, 96, -415.0 / 6}};
-  for (int t = 0; t < 5; ++t) {
-    for (int k = 0; k < 5; ++k) { g.d1x[t][k] = c1[t][k] / (12 * g.dksi); g.d1y[t][k] = c1[t][k] / (12 * g.deta); }
-    for (int k = 0; k < 6; ++k) { g.d2x[t][k] = c2[t][k] / (12 * g.dksi2); g.d2y[t][k] = c2[t][k] / (12 * g.deta2); }
-  }
+  const double c1[5] = {1, -8, 0, 8, -1};
+  for (int k = 0; k < 5; ++k) { g.c1x[k] = c1[k] / (12 * g.dksi); g.c1y[k] = c1[k] / (12 * g.deta); }
+  g.tab = tab;
   return g;
 }
 
@@ -46,19 +62,19 @@ inline MeshGeom make_geom(const MeshParams& mp, int nx, int ny) {
 JF_HD double d_ksi(const MeshGeom& g, const double* f, int r, int c) {
   int t = fd_type(c, g.nx), s = d1_start(c, g.nx, t);
   const double* p = f + (size_t)r * g.nx + s;
-  const double* w = g.d1x[t];
+  const double* w = g.tab->d1x + t * 5;
   return w[0] * p[0] + w[1] * p[1] + w[2] * p[2] + w[3] * p[3] + w[4] * p[4];
 }
 JF_HD double d_eta(const MeshGeom& g, const double* f, int r, int c) {
   int t = fd_type(r, g.ny), s = d1_start(r, g.ny, t);
   const double* p = f + (size_t)s * g.nx + c;
-  const double* w = g.d1y[t];
+  const double* w = g.tab->d1y + t * 5;
   size_t n = g.nx;
   return w[0] * p[0] + w[1] * p[n] + w[2] * p[2 * n] + w[3] * p[3 * n] + w[4] * p[4 * n];
 }
 JF_HD double d2_ksi(const MeshGeom& g, const double* f, int r, int c) {
   int t = fd_type(c, g.nx), s = d2_start(c, g.nx, t), cnt = d2_count(t);
-  const double* w = g.d2x[t];
+  const double* w = g.tab->d2x + t * 6;
   if (t == 4) { s += 1; w += 1; cnt = 5; } // last row touches only the last 5 columns
   const double* p = f + (size_t)r * g.nx + s;
   double acc = 0.0;
@@ -67,7 +83,7 @@ JF_HD double d2_ksi(const MeshGeom& g, const double* f, int r, int c) {
 }
 JF_HD double d2_eta(const MeshGeom& g, const double* f, int r, int c) {
   int t = fd_type(r, g.ny), s = d2_start(r, g.ny, t), cnt = d2_count(t);
-  const double* w = g.d2y[t];
+  const double* w = g.tab->d2y + t * 6;
   if (t == 4) { s += 1; w += 1; cnt = 5; }
   const double* p = f + (size_t)s * g.nx + c;
   double acc = 0.0;
@@ -78,8 +94,8 @@ JF_HD double d2_eta(const MeshGeom& g, const double* f, int r, int c) {
 JF_HD double d_ksieta(const MeshGeom& g, const double* f, int r, int c) {
   int ty = fd_type(r, g.ny), sy = d1_start(r, g.ny, ty);
   int tx = fd_type(c, g.nx), sx = d1_start(c, g.nx, tx);
-  const double* wy = g.d1y[ty];
-  const double* wx = g.d1x[tx];
+  const double* wy = g.tab->d1y + ty * 5;
+  const double* wx = g.tab->d1x + tx * 5;
   double acc = 0.0;
   for (int a = 0; a < 5; ++a) {
     const double* p = f + (size_t)(sy + a) * g.nx + sx;
@@ -179,19 +195,19 @@ JF_HD void mesh_laplace_interior(const MeshGeom& g, const double* const* M, cons
 #undef AX
 #undef AY
   // centred first derivative weights (row type 2), columns / rows -2,-1,+1,+2 (the weight of 0 is 0)
-  const double* wx = g.d1x[2];
-  const double* wy = g.d1y[2];
+  const double* wx = g.c1x;
+  const double* wy = g.c1y;
   const ptrdiff_t sx = (ptrdiff_t)nx;
   // D_ksi(A12 * D_eta v): sum_k wx[k] * A12(r, c+k-2) * sum_a wy[a] v(r+a-2, c+k-2)
   double accx = 0.0, accy = 0.0;
-#pragma unroll
+JF_UNROLL
   for (int k = 0; k < 5; ++k) {
     if (k == 2) continue;
     const double* q = p + (k - 2);
     double ve = wy[0] * q[-2 * sx] + wy[1] * q[-sx] + wy[2] * q[0] + wy[3] * q[sx] + wy[4] * q[2 * sx];
     accx += wx[k] * (A12[k - 2] * ve);
   }
-#pragma unroll
+JF_UNROLL
   for (int k = 0; k < 5; ++k) {
     if (k == 2) continue;
     const double* q = p + (ptrdiff_t)(k - 2) * sx;
@@ -220,7 +236,7 @@ JF_HD void mesh_laplace_point(const MeshGeom& g, const double* const* M, const d
   // B.2: D_ksi(A12 v_eta) with left/right columns zeroed ; D_eta(A12 v_ksi) with top/bottom rows zeroed
   if (c != 0 && c != g.nx - 1) {
     int t = fd_type(c, g.nx), s = d1_start(c, g.nx, t);
-    const double* w = g.d1x[t];
+    const double* w = g.tab->d1x + t * 5;
     double acc = 0.0;
     for (int k = 0; k < 5; ++k) {
       if (w[k] == 0.0) continue;
@@ -231,7 +247,7 @@ JF_HD void mesh_laplace_point(const MeshGeom& g, const double* const* M, const d
   }
   if (r != 0 && r != g.ny - 1) {
     int t = fd_type(r, g.ny), s = d1_start(r, g.ny, t);
-    const double* w = g.d1y[t];
+    const double* w = g.tab->d1y + t * 5;
     double acc = 0.0;
     for (int k = 0; k < 5; ++k) {
       if (w[k] == 0.0) continue;

@@ -13,7 +13,6 @@ state it closes over (``Uo``, ``k``, ``g``, ``L`` ... / ``U.val``, ``dt``, ``CN_
 from __future__ import annotations
 
 import ctypes as C
-import math
 
 import numpy as np
 
@@ -30,8 +29,8 @@ class _DeviceResidual:
                  kernel_variant=0, buffers=None):
         # gs: Gram-Schmidt variant of the Arnoldi process.  SciPy uses modified GS (j dependent reductions per
         # step); the device path batches all dots of a step into one fused reduction (classical GS) and takes a
-        # second pass only when ||w_after|| < gs_tau ||w_before|| (cancellation of more than 1/gs_tau), decided on
-        # the device.  "cgs2" always re-orthogonalises, "cgs" never does.
+        # second pass only when ||w_after|| < gs_tau ||w_before|| (cancellation of more than 1/gs_tau), decided from
+        # the scalars the host reads back once per Arnoldi step.  "cgs2" always re-orthogonalises, "cgs" never does.
         self.nx, self.ny = int(nx), int(ny)
         self.comm = comm
         self._krylov = (int(inner_m), int(outer_k))

@@ -256,14 +256,14 @@ class HostOps : public DeviceOps {
   // ---- moving mesh ---------------------------------------------------------------------------------
   void mesh_metrics(const MeshParams& mp, const double* Q, double* const* M) override {
     launches_++;
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     for (int r = 0; r < g_.ny; ++r)
       for (int c = 0; c < g_.nx; ++c) mesh_metrics_point(gm, Q, r, c, M);
   }
   void mesh_laplace(const MeshParams& mp, const double* const* M, const double* v, double* vxx, double* vyy,
                     int sum_only, int deriv_bc) override {
     launches_++;
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     for (int r = 0; r < g_.ny; ++r)
       for (int c = 0; c < g_.nx; ++c) {
         double xx, yy;
@@ -303,7 +303,7 @@ class HostOps : public DeviceOps {
   void droplet_flux(const MeshParams& mp, const DropletParams& dp, const double* const* M, const double* p,
                     const double* h, double* A, double* B) override {
     launches_++;
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     for (int r = 0; r < g_.ny; ++r)
       for (int c = 0; c < g_.nx; ++c) {
         size_t e = (size_t)r * g_.nx + c;
@@ -312,7 +312,7 @@ class HostOps : public DeviceOps {
   }
   void droplet_div(const MeshParams& mp, const double* const* M, const double* A, const double* B, double* out) override {
     launches_++;
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     for (int r = 0; r < g_.ny; ++r)
       for (int c = 0; c < g_.nx; ++c) out[(size_t)r * g_.nx + c] = droplet_div_point(gm, M, A, B, r, c);
   }
@@ -330,7 +330,7 @@ class HostOps : public DeviceOps {
   }
   void pma_smooth(const MeshParams& mp, const double* in, double* out) override {
     launches_++;
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     for (int r = 0; r < g_.ny; ++r)
       for (int c = 0; c < g_.nx; ++c) out[(size_t)r * g_.nx + c] = pma_smooth_point(gm, in, r, c);
   }
@@ -366,13 +366,15 @@ class HostOps : public DeviceOps {
   }
   void pma_spectral_divide(const MeshParams& mp, double gamma, double* Y) override {
     launches_++;
-    MeshGeom gm = make_geom(mp, g_.nx, g_.ny);
+    MeshGeom gm = geom(mp);
     for (int r = 0; r < g_.ny; ++r)
       for (int c = 0; c < g_.nx; ++c) { size_t e = (size_t)r * g_.nx + c; Y[e] = Y[e] / (1.0 - gamma * pma_leig(gm, r, c)); }
   }
 
   void set_comm(hostsim_allreduce_fn ar, hostsim_halo_fn halo, void* user) { ar_ = ar; halo_ = halo; user_ = user; }
   std::vector<double> dctx_, dcty_;
+  MeshTables htab_;
+  MeshGeom geom(const MeshParams& mp) { fill_mesh_tables(mp, htab_); return make_geom(mp, g_.nx, g_.ny, &htab_); }
 
  private:
   Grid g_;
