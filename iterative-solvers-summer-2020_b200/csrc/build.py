@@ -27,7 +27,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     cmd = [_nvcc(), "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
-           "-Xcompiler", "-Wno-unused-function", "-cudart", "static"] + ARCH
+           "-Xcompiler", "-Wno-unused-function", "-Xcompiler", "-Wno-unknown-pragmas", "-cudart", "static"] + ARCH
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-I", HERE, "-o", LIB] + [os.path.join(HERE, s) for s in SOURCES] + ["-ldl", "-Xlinker", "-Bsymbolic"]
