@@ -292,7 +292,11 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"swift-hohenberg {N}^2 periodic, h={H}, k=0.2, r=0.01, g=1, seeded N(0,1) state",
                    "solver": f"newton_krylov/LGMRES inner_m=30 outer_k=10, gs={args.gs} tau={args.gs_tau}",
-                   "parallelism": f"row slabs x{world}", "l2": "inputs exceed L2 (2.1 GB per field)" if N >= 8192 else "inputs may fit L2",
+                   "parallelism": f"row slabs x{world}",
+                   "collectives": ("none (one rank)" if world == 1 else
+                                   "peer memory over NVLink (direct halo stores + one-shot all-reduce kernels)" if ctx.peer_memory()
+                                   else "NCCL send/recv + ncclAllReduce"),
+                   "l2": "inputs exceed L2 (2.1 GB per field)" if N >= 8192 else "inputs may fit L2",
                    "newton_its_per_step": nit, "f_evals_per_step": nfev, "arnoldi_its_per_step": inner,
                    "second_gs_passes_per_step": reorth},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,

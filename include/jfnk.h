@@ -129,6 +129,10 @@ int jfnk_set_callback(jfnk_ctx* ctx, jfnk_callback cb, void* user);
 /* rank 0 fills a 128-byte NCCL unique id; the host layer broadcasts it (torch.distributed). */
 int jfnk_comm_unique_id(void* id128);
 int jfnk_comm_init(jfnk_ctx* ctx, const void* id128);
+/* 1 when the ranks of this communicator exchange halos and reduce the Krylov scalars through peer memory (CUDA IPC over
+ * NVLink: direct stores into the neighbours' halo buffers, one-shot all-reduce), 0 when they use the NCCL send/recv +
+ * ncclAllReduce path (single rank, IPC unavailable, or JFNK_P2P=0 in the environment). */
+int jfnk_comm_peer_memory(jfnk_ctx* ctx);
 
 /* ---- Swift-Hohenberg (sh_scipy_nk.py:15-39) --------------------------------------------------- */
 /* h = mesh spacing d/N, r,g = PDE parameters, k = time step. */
@@ -212,6 +216,10 @@ int jfnk_profile_read(jfnk_ctx* ctx, jfnk_kernel_stat* out, int cap, int* count)
  * out[i] = V_i . w (i<nv), out[nv] = w.w ; V = nv vectors `stride` doubles apart starting at dV. */
 int jfnk_multi_dot(jfnk_ctx* ctx, int nv, const double* dV, size_t stride, const double* dw, double* out_host);
 /* w -= sum_i coef_host[i] V_i ; returns ||w||^2 in *nrm2_host. */
+/* Micro-benchmark of the slab collectives (multi-rank contexts; every rank must call it): enqueues `reps` back-to-back
+ * all-reduces of `count` (<= 48) fp64 scalars (what = 0) or halo exchanges of the 2-row halos of dfield (what = 1) and
+ * returns the host-clock time per operation in microseconds (stream drained before and after). */
+int jfnk_comm_bench(jfnk_ctx* ctx, int what, int count, const double* dfield, int reps, double* usec_host);
 int jfnk_multi_axpy(jfnk_ctx* ctx, int nv, const double* dV, size_t stride, const double* coef_host, double* dw,
                     double* nrm2_host);
 

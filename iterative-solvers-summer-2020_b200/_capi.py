@@ -64,6 +64,8 @@ SIGNATURES = {
     "jfnk_set_callback": (C.c_int, [_CTX, CALLBACK, C.c_void_p]),
     "jfnk_comm_unique_id": (C.c_int, [C.c_void_p]),
     "jfnk_comm_init": (C.c_int, [_CTX, C.c_void_p]),
+    "jfnk_comm_peer_memory": (C.c_int, [_CTX]),
+    "jfnk_comm_bench": (C.c_int, [_CTX, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_double)]),
     "jfnk_sh_setup": (C.c_int, [_CTX, C.c_double, C.c_double, C.c_double, C.c_double]),
     "jfnk_spmv_lap": (C.c_int, [_CTX, _P, _P]),
     "jfnk_spmv_sh": (C.c_int, [_CTX, _P, _P]),

@@ -151,6 +151,20 @@ class Context:
     def launches(self):
         return int(self.lib.jfnk_launch_count(self.handle))
 
+    def comm_bench(self, what, count=32, field=None, reps=200):
+        """microseconds per all-reduce of ``count`` scalars (what="allreduce") or per 2-row halo exchange of the device
+        vector ``field`` (what="halo"), back to back on the stream; collective over the slab ranks."""
+        us = C.c_double(0.0)
+        w = {"allreduce": 0, "halo": 1}[what]
+        self.check(self.lib.jfnk_comm_bench(self.handle, w, int(count), self.buf.ptr(field) if field is not None else None,
+                                            int(reps), C.byref(us)))
+        return us.value
+
+    def peer_memory(self):
+        """True when the slab ranks talk through peer memory (direct NVLink stores + one-shot all-reduce)
+        rather than NCCL send/recv + ncclAllReduce."""
+        return bool(self.lib.jfnk_comm_peer_memory(self.handle))
+
     # -- BLAS-1 building blocks of the Arnoldi process (exposed for micro-benchmarks and unit parity) ----
     def multi_dot(self, dV, nv, stride, dw):
         """host array [V_0.w, ..., V_{nv-1}.w, w.w] for nv device vectors `stride` doubles apart in dV."""

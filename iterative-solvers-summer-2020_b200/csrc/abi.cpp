@@ -1,4 +1,5 @@
 // extern "C" boundary of libjfnk.so (include/jfnk.h).  No exception crosses it.
+#include <chrono>
 #include <math.h>
 #include <string.h>
 #include <new>
@@ -111,6 +112,11 @@ int jfnk_comm_init(jfnk_ctx* ctx, const void* id128) {
   JF_CATCH
 }
 
+int jfnk_comm_peer_memory(jfnk_ctx* ctx) {
+  if (!ctx || !ctx->ops) return 0;
+  return backend_peer_memory(ctx->ops);
+}
+
 int jfnk_sh_setup(jfnk_ctx* ctx, double h, double r, double g, double k) {
   JF_TRY JF_CHECK_CTX(ctx); return done(ctx, ctx->eng->sh_setup(h, r, g, k)); JF_CATCH
 }
@@ -218,6 +224,24 @@ int jfnk_multi_dot(jfnk_ctx* ctx, int nv, const double* dV, size_t stride, const
   ctx->ops->mdot(nv, V, dw, JS_RD);
   ctx->ops->allreduce_sum(JS_RD, nv + 1);
   if (out_host) ctx->ops->read_scalars(JS_RD, nv + 1, out_host);
+  return done(ctx, ctx->ops->status());
+  JF_CATCH
+}
+
+int jfnk_comm_bench(jfnk_ctx* ctx, int what, int count, const double* dfield, int reps, double* usec_host) {
+  JF_TRY JF_CHECK_CTX(ctx);
+  if (reps < 1 || !usec_host || (what == 0 && (count < 1 || count > JF_MAXV)) || (what == 1 && !dfield) || what < 0 || what > 1)
+    return set_err(JFNK_INVALID, "jfnk_comm_bench: bad arguments");
+  double dummy;
+  ctx->ops->read_scalars(JS_TMP0, 1, &dummy); // drain the stream
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < reps; ++i) {
+    if (what == 0) ctx->ops->allreduce_sum(JS_RD2, count);
+    else ctx->ops->sh_bind_x0(dfield);
+  }
+  ctx->ops->read_scalars(JS_TMP0, 1, &dummy);
+  auto t1 = std::chrono::steady_clock::now();
+  *usec_host = std::chrono::duration<double, std::micro>(t1 - t0).count() / reps;
   return done(ctx, ctx->ops->status());
   JF_CATCH
 }

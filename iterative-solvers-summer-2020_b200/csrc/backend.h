@@ -10,4 +10,5 @@ int backend_device_ok(std::string& why);
 DeviceOps* backend_make_ops(const jfnk_config& cfg, std::string& why, int& code);
 int backend_unique_id(void* id128, std::string& why);
 int backend_comm_init(DeviceOps* ops, const void* id128, std::string& why);
+int backend_peer_memory(DeviceOps* ops);
 } // namespace jfnk

@@ -28,6 +28,9 @@ __device__ __forceinline__ double2 ldg2(const double* p) {
 __device__ __forceinline__ double ldg1(const double* p) { return __ldg(p); }
 __device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
 
+// x + a*v exactly as NumPy evaluates `x0 + sc*v` (product rounded, then sum rounded; never contracted to an FMA)
+__device__ __forceinline__ double combine(double x, double a, double v) { return __dadd_rn(x, __dmul_rn(a, v)); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

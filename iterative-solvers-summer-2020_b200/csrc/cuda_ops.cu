@@ -13,8 +13,10 @@
 #include "backend.h"
 #include "blas_kernels.cuh"
 #include "mesh_kernels.cuh"
+#include "mesh_march.cuh"
 #include "pma_kernels.cuh"
 #include "nccl_dl.h"
+#include "p2p_kernels.cuh"
 #include "sh_kernels.cuh"
 
 namespace jfnk {
@@ -25,10 +27,10 @@ inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 // kernel classes of the per-kernel timing (bench.py roofline); bytes are the ALGORITHMIC bytes of DESIGN.md
 enum KClass { K_MDOT = 0, K_GS_UPDATE, K_MAXPY, K_LINCOMB, K_SPMV_LAP, K_SPMV_L, K_SET_PREV, K_RESIDUAL, K_JVP,
-              K_SHLIN, K_MESH, K_SCALAR, K_MDOT2, K_GS_UPDATE2, K_COUNT };
+              K_SHLIN, K_MESH, K_SCALAR, K_MDOT2, K_GS_UPDATE2, K_HALO, K_ALLREDUCE, K_COUNT };
 const char* const kClassName[K_COUNT] = {"mdot", "gs_update", "maxpy", "lincomb", "spmv_lap", "spmv_L", "set_prev",
                                          "sh_residual", "sh_jvp", "shlin", "mesh", "scalar", "mdot_pass2",
-                                         "gs_update_pass2"};
+                                         "gs_update_pass2", "halo_exchange", "allreduce"};
 
 class CudaOps : public DeviceOps {
  public:
@@ -45,7 +47,7 @@ class CudaOps : public DeviceOps {
     if (!ck(cudaMalloc(&ws_.partials, sizeof(double) * (size_t)kMaxBlocks * kPartialStride), "cudaMalloc(partials)")) { why = err_; return; }
     if (!ck(cudaMalloc(&ws_.ticket, sizeof(unsigned)), "cudaMalloc(ticket)")) { why = err_; return; }
     if (!ck(cudaMemsetAsync(ws_.ticket, 0, sizeof(unsigned), stream_), "cudaMemset(ticket)")) { why = err_; return; }
-    if (!ck(cudaMallocHost(&pinned_, sizeof(double) * JS_COUNT), "cudaMallocHost")) { why = err_; return; }
+    if (!ck(cudaMallocHost(&pinned_, sizeof(double) * (JS_COUNT + 1)), "cudaMallocHost")) { why = err_; return; }
     if (g_.nranks > 1) {
       // row halos of the linearisation point (x0), of the operand vector (z / dx) and of a generic field
       size_t hb = sizeof(double) * 2 * (size_t)g_.nx;
@@ -55,6 +57,9 @@ class CudaOps : public DeviceOps {
     ok = true;
   }
   ~CudaOps() override {
+    if (graph_exec_) { cudaStreamSynchronize(stream_); cudaGraphExecDestroy(graph_exec_); }
+    if (cap_stream_) cudaStreamDestroy(cap_stream_);
+    p2p_teardown();
     if (comm_ && nccl_) nccl_->CommDestroy(comm_);
     for (auto& r : recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : free_events_) cudaEventDestroy(e);
@@ -120,20 +125,72 @@ class CudaOps : public DeviceOps {
   }
   const char* last_error() const override { return err_.c_str(); }
 
+  // ---- CUDA graph capture of a fixed launch sequence (mesh relaxation passes) ----------------------------------
+  bool graph_begin() override {
+    if (profiling_ || capturing_) return false; // per-launch events cannot be timed inside a capture
+    static const bool off = getenv("JFNK_GRAPHS") && atoi(getenv("JFNK_GRAPHS")) == 0;
+    if (off || status() != JFNK_OK) return false;
+    // Record on a private stream (the caller's may be the legacy default stream, which cannot be captured); nothing
+    // executes while recording, and the replays are launched on the caller's stream.
+    if (!cap_stream_ && cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); cap_stream_ = nullptr; return false; }
+    if (cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    user_stream_ = stream_;
+    stream_ = cap_stream_;
+    capturing_ = true;
+    capture_launch0_ = launches_;
+    return true;
+  }
+  void graph_end_launch(int replays) override {
+    if (!capturing_) return;
+    capturing_ = false;
+    stream_ = user_stream_;
+    cudaGraph_t graph = nullptr;
+    if (!ck(cudaStreamEndCapture(cap_stream_, &graph), "cudaStreamEndCapture")) return;
+    const int64_t per_replay = launches_ - capture_launch0_;
+    launches_ = capture_launch0_;
+    if (graph_exec_) { // the previous replay may still be running: drain before releasing it
+      cudaStreamSynchronize(stream_);
+      cudaGraphExecDestroy(graph_exec_);
+      graph_exec_ = nullptr;
+    }
+    bool ok = ck(cudaGraphInstantiate(&graph_exec_, graph, 0), "cudaGraphInstantiate");
+    cudaGraphDestroy(graph);
+    if (!ok) return;
+    for (int i = 0; i < replays; ++i)
+      if (!ck(cudaGraphLaunch(graph_exec_, stream_), "cudaGraphLaunch")) return;
+    launches_ += per_replay * replays;
+    graph_replays_ += replays;
+  }
+
   // ---- scalars ----------------------------------------------------------------------------------
   void read_scalars(int off, int cnt, double* host) override {
     if (!ck(cudaMemcpyAsync(pinned_, S_ + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, stream_), "D2H scalars")) return;
+    int* perr = reinterpret_cast<int*>(pinned_ + JS_COUNT);
+    if (p2p_) ck(cudaMemcpyAsync(perr, p2p_err(), sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H peer flag");
     if (!ck(cudaStreamSynchronize(stream_), "cudaStreamSynchronize")) return;
     memcpy(host, pinned_, sizeof(double) * cnt);
+    if (p2p_ && *perr && code_ == JFNK_OK) {
+      code_ = JFNK_NCCL_ERROR;
+      err_ = "peer-memory collective timed out: a rank did not reach the matching halo exchange / all-reduce";
+    }
   }
   void write_scalars(int off, int cnt, const double* host) override {
     ck(cudaMemcpyAsync(S_ + off, host, sizeof(double) * cnt, cudaMemcpyHostToDevice, stream_), "H2D scalars");
   }
   void allreduce_sum(int off, int cnt) override {
-    if (g_.nranks > 1) nck(nccl_->AllReduce(S_ + off, S_ + off, cnt, ncclDouble, ncclSum, comm_, stream_), "ncclAllReduce(sum)");
+    if (g_.nranks == 1) return;
+    if (p2p_ && cnt <= kP2PMaxScalars) { p2p_allreduce(off, cnt, 0, -1, 0, 0); return; }
+    nck(nccl_->AllReduce(S_ + off, S_ + off, cnt, ncclDouble, ncclSum, comm_, stream_), "ncclAllReduce(sum)");
   }
   void allreduce_max(int off, int cnt) override {
-    if (g_.nranks > 1) nck(nccl_->AllReduce(S_ + off, S_ + off, cnt, ncclDouble, ncclMax, comm_, stream_), "ncclAllReduce(max)");
+    if (g_.nranks == 1) return;
+    if (p2p_ && cnt <= kP2PMaxScalars) { p2p_allreduce(off, cnt, 1, -1, 0, 0); return; }
+    nck(nccl_->AllReduce(S_ + off, S_ + off, cnt, ncclDouble, ncclMax, comm_, stream_), "ncclAllReduce(max)");
+  }
+  void allreduce_sum_givens(int off, int cnt, int j, int taken, int rerun) override {
+    if (g_.nranks > 1 && p2p_ && cnt <= kP2PMaxScalars) { p2p_allreduce(off, cnt, 0, j, taken, rerun); return; }
+    allreduce_sum(off, cnt);
+    givens(j, taken, rerun);
   }
 
   // ---- BLAS-1 -------------------------------------------------------------------------------------
@@ -269,6 +326,33 @@ class CudaOps : public DeviceOps {
     if (g_.nranks == 1) {
       top = v + (size_t)(g_.nrows - 2) * g_.nx;
       bot = v;
+      return;
+    }
+    if (p2p_) {
+      if (exchange) {
+        const unsigned long long e = ++halo_epoch_[slot];
+        const int par = (int)(e & 1ull);
+        const int prev = (g_.rank + g_.nranks - 1) % g_.nranks, next = (g_.rank + 1) % g_.nranks;
+        P2PHaloArgs A;
+        A.src_first = v;
+        A.src_last = v + (size_t)(g_.nrows - 2) * g_.nx;
+        A.dst_prev_bot = p2p_halo(prev, slot, par, 1);
+        A.dst_next_top = p2p_halo(next, slot, par, 0);
+        A.flag_prev_bot = p2p_hflag(prev, slot, 1);
+        A.flag_next_top = p2p_hflag(next, slot, 0);
+        A.my_flag_top = p2p_hflag(g_.rank, slot, 0);
+        A.my_flag_bot = p2p_hflag(g_.rank, slot, 1);
+        A.epoch = e;
+        A.count = 2 * (size_t)g_.nx;
+        A.ticket = ws_.ticket;
+        A.err = p2p_err();
+        const int blocks = (int)std::max<size_t>(1, std::min<size_t>(32, (A.count + 1023) / 1024));
+        Prof prof(this, K_HALO, 4.0 * 8.0 * (double)A.count); // two messages out, two in
+        p2p_halo_kernel<<<blocks, 256, 0, stream_>>>(A);
+      }
+      const int par = (int)(halo_epoch_[slot] & 1ull);
+      top = p2p_halo(g_.rank, slot, par, 0);
+      bot = p2p_halo(g_.rank, slot, par, 1);
       return;
     }
     double* t = halo_[2 * slot];
@@ -418,8 +502,70 @@ class CudaOps : public DeviceOps {
     Prof prof(this, K_MESH, nb(8));
     mesh_metrics_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, Q, P);
   }
+  // ---- marching Laplace_operator (mesh_march.cuh): large grids, or kernel_variant == 2 ----
+  bool use_march() const {
+    if (variant_ == 1 || g_.nx < 16 || g_.ny < 16) return false;
+    return variant_ == 2 || g_.n() >= (size_t)256 * 256; // small grids are launch-latency bound: one thread per point
+  }
+  template <int MODE, bool HAS_V>
+  void march_launch(MarchArgs& A, const MeshParams& mp, double vecs) {
+    A.gm = geom(mp);
+    int& per_sm = occupancy_[reinterpret_cast<const void*>(mesh_march_kernel<MODE, HAS_V>)];
+    if (per_sm == 0) {
+      int nb_ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, mesh_march_kernel<MODE, HAS_V>, kMarchThreads, 0) != cudaSuccess || nb_ < 1) nb_ = 1;
+      per_sm = nb_;
+    }
+    // all CTAs resident at once: a few frame CTAs (general per-point path) + strips x row chunks of the interior
+    const long long target = std::min<long long>((long long)sms_ * per_sm, kMaxBlocks);
+    const long long nf = 8LL * g_.nx + 8LL * (g_.ny - 8);
+    const int rows = g_.ny - 8;
+    A.nstrips = (g_.nx - 8 + kMarchOut - 1) / kMarchOut;
+    A.nframe_ctas = (int)std::max<long long>(1, std::min<long long>((nf + kMarchThreads - 1) / kMarchThreads, target / 8));
+    long long chunks = std::max<long long>(1, (target - A.nframe_ctas) / A.nstrips);
+    A.rows_per_chunk = std::max<int>(kMarchMinRows, (int)((rows + chunks - 1) / chunks));
+    const int nchunks = (rows + A.rows_per_chunk - 1) / A.rows_per_chunk;
+    static const int dbg = getenv("JFNK_MARCH_DEBUG") ? atoi(getenv("JFNK_MARCH_DEBUG")) : 0;
+    A.debug_skip = (MODE == MARCH_PMA2_RESID) ? 0 : dbg; // (the reduction of RESID needs every CTA)
+    Prof prof(this, K_MESH, nb(vecs));
+    mesh_march_kernel<MODE, HAS_V><<<A.nframe_ctas + A.nstrips * nchunks, kMarchThreads, 0, stream_>>>(A, S_, ws_);
+  }
+  MarchArgs march_args(const double* const* M, const double* x, const double* v, ScalarRef a, double* out) {
+    MarchArgs A;
+    memset(&A, 0, sizeof(A));
+    A.M = cptrs(M);
+    A.x = x; A.v = v; A.a = a; A.pa = sref(0.0); A.div = sref(1.0);
+    A.out = out;
+    return A;
+  }
+  void pma2_eval(const MeshParams& mp, const Pma2Params& pp, const double* const* M, const double* x, const double* v,
+                 ScalarRef a, const double* uval, const double* cn, const double* f0, ScalarRef div,
+                 double* const* scratch, double* xt_out, double* out, int norm_off) override {
+    if (!use_march()) {
+      pma2_eval_unfused(mp, pp, M, x, v, a, uval, cn, f0, div, scratch, xt_out, out, norm_off);
+      return;
+    }
+    // pass 1: lap1 = Laplace(x + a v) (+ the trial iterate when the caller keeps it)
+    MarchArgs A = march_args(M, x, v, a, scratch[0]);
+    A.out2 = (v && !f0) ? xt_out : nullptr;
+    if (v) march_launch<MARCH_LAP, true>(A, mp, 7.0 + (A.out2 ? 1.0 : 0.0));
+    else march_launch<MARCH_LAP, false>(A, mp, 6.0);
+    // pass 2: Laplace(lap1) with the pointwise PMA2 terms, the Crank-Nicolson combination and the FD quotient fused in
+    MarchArgs B = march_args(M, scratch[0], nullptr, sref(0.0), out);
+    B.px = x; B.pv = v; B.pa = a; B.uval = uval; B.cn = cn; B.f0 = f0; B.div = div; B.pp = pp; B.norm_off = norm_off;
+    const double vecs = 9.0 + (v ? 1.0 : 0.0) + (f0 ? 1.0 : 0.0); // lap1, 4 metric fields, x, (v), uval, cn, (f0); out
+    if (f0) march_launch<MARCH_PMA2_JVP, false>(B, mp, vecs);
+    else march_launch<MARCH_PMA2_RESID, false>(B, mp, vecs);
+  }
+
   void mesh_laplace(const MeshParams& mp, const double* const* M, const double* v, double* vxx, double* vyy,
                     int sum_only, int deriv_bc) override {
+    if (sum_only && use_march()) {
+      MarchArgs A = march_args(M, v, nullptr, sref(0.0), vxx);
+      A.deriv_bc = deriv_bc;
+      march_launch<MARCH_LAP, false>(A, mp, 6.0);
+      return;
+    }
     MeshGeom gm = geom(mp);
     Prof prof(this, K_MESH, nb(sum_only ? 6 : 7));
     mesh_laplace_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), v, vxx, vyy, sum_only, deriv_bc);
@@ -510,7 +656,100 @@ class CudaOps : public DeviceOps {
     memcpy(&id, id128, sizeof(id));
     ncclResult_t r = nccl_->CommInitRank(&comm_, g_.nranks, id, g_.rank);
     if (r != ncclSuccess) { why = std::string("ncclCommInitRank: ") + nccl_->GetErrorString(r); comm_ = nullptr; return JFNK_NCCL_ERROR; }
+    return p2p_setup(why);
+  }
+  bool peer_memory() const { return p2p_; }
+
+  // ---- peer memory (CUDA IPC over NVLink) ---------------------------------------------------------------------
+  // One library-owned block per rank: halo buffers [slot][parity][top|bot][2 nx], all-reduce mailboxes
+  // [parity][rank][64], arrival flags and an error word; every rank maps every peer's block.
+  size_t p2p_halo_doubles() const { return 2 * (size_t)g_.nx; }
+  size_t p2p_off_mail() const { return sizeof(double) * p2p_halo_doubles() * kP2PHaloSlots * 2 * 2; }
+  size_t p2p_off_flags() const { return p2p_off_mail() + sizeof(double) * 2 * kP2PMaxRanks * kP2PMaxScalars; }
+  size_t p2p_off_err() const { return p2p_off_flags() + sizeof(unsigned long long) * (kP2PHaloSlots * 2 + kP2PMaxRanks); }
+  size_t p2p_bytes() const { return p2p_off_err() + 64; }
+  double* p2p_halo(int rank, int slot, int par, int dir) const {
+    return reinterpret_cast<double*>(peer_[rank]) + p2p_halo_doubles() * (size_t)((slot * 2 + par) * 2 + dir);
+  }
+  double* p2p_mail(int rank, int par) const {
+    return reinterpret_cast<double*>(peer_[rank] + p2p_off_mail()) + (size_t)par * kP2PMaxRanks * kP2PMaxScalars;
+  }
+  unsigned long long* p2p_hflag(int rank, int slot, int dir) const {
+    return reinterpret_cast<unsigned long long*>(peer_[rank] + p2p_off_flags()) + slot * 2 + dir;
+  }
+  unsigned long long* p2p_rflags(int rank) const {
+    return reinterpret_cast<unsigned long long*>(peer_[rank] + p2p_off_flags()) + kP2PHaloSlots * 2;
+  }
+  int* p2p_err() const { return reinterpret_cast<int*>(peer_[g_.rank] + p2p_off_err()); }
+
+  void p2p_allreduce(int off, int cnt, int op, int givens_j, int taken, int rerun) {
+    const unsigned long long e = ++reduce_epoch_;
+    const int par = (int)(e & 1ull);
+    P2PReduceArgs A;
+    memset(&A, 0, sizeof(A));
+    A.S = S_; A.off = off; A.cnt = cnt; A.op = op; A.rank = g_.rank; A.nranks = g_.nranks;
+    for (int q = 0; q < g_.nranks; ++q) { A.mailbox_peer[q] = p2p_mail(q, par); A.flags_peer[q] = p2p_rflags(q); }
+    A.my_mailbox = p2p_mail(g_.rank, par);
+    A.my_flags = p2p_rflags(g_.rank);
+    A.epoch = e;
+    A.givens_j = givens_j; A.givens_taken = taken; A.givens_rerun = rerun;
+    A.err = p2p_err();
+    Prof prof(this, K_ALLREDUCE, 8.0 * cnt * g_.nranks);
+    p2p_allreduce_kernel<<<1, kP2PMaxScalars, 0, stream_>>>(A);
+  }
+
+  // Collective over the NCCL communicator.  Every rank always runs both collectives below, carrying its local
+  // success flag, so that a rank on which IPC is unavailable (e.g. a VMM-backed allocator, no peer access) makes ALL
+  // ranks fall back to the NCCL send/recv + ncclAllReduce path together.  JFNK_P2P=0 disables peer memory.
+  int p2p_setup(std::string& why) {
+    const char* env = getenv("JFNK_P2P");
+    int ok = !(env && atoi(env) == 0) && g_.nranks <= kP2PMaxRanks;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaMalloc(&p2p_block_, p2p_bytes()) != cudaSuccess) { ok = 0; p2p_block_ = nullptr; }
+    if (ok && cudaMemset(p2p_block_, 0, p2p_bytes()) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, p2p_block_) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    std::vector<cudaIpcMemHandle_t> all(g_.nranks);
+    char* stage = nullptr;
+    int* dflag = nullptr;
+    if (!ck(cudaMalloc(&stage, hb * g_.nranks + sizeof(int)), "cudaMalloc(ipc staging)")) { why = err_; return JFNK_CUDA_ERROR; }
+    dflag = reinterpret_cast<int*>(stage + hb * g_.nranks);
+    ck(cudaMemcpyAsync(stage + hb * g_.rank, &mine, hb, cudaMemcpyHostToDevice, stream_), "H2D ipc handle");
+    nck(nccl_->AllGather(stage + hb * g_.rank, stage, hb, ncclChar, comm_, stream_), "ncclAllGather(ipc handles)");
+    ck(cudaMemcpyAsync(all.data(), stage, hb * g_.nranks, cudaMemcpyDeviceToHost, stream_), "D2H ipc handles");
+    ck(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");
+    if (code_ != JFNK_OK) { cudaFree(stage); why = err_; return code_; }
+    for (int q = 0; q < kP2PMaxRanks; ++q) peer_[q] = nullptr;
+    if (ok) {
+      peer_[g_.rank] = reinterpret_cast<char*>(p2p_block_);
+      for (int q = 0; q < g_.nranks && ok; ++q) {
+        if (q == g_.rank) continue;
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+        peer_[q] = reinterpret_cast<char*>(p);
+      }
+    }
+    ck(cudaMemcpyAsync(dflag, &ok, sizeof(int), cudaMemcpyHostToDevice, stream_), "H2D ipc flag");
+    nck(nccl_->AllReduce(dflag, dflag, 1, ncclInt, ncclMin, comm_, stream_), "ncclAllReduce(ipc agreement)");
+    int agreed = 0;
+    ck(cudaMemcpyAsync(&agreed, dflag, sizeof(int), cudaMemcpyDeviceToHost, stream_), "D2H ipc flag");
+    ck(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");
+    cudaFree(stage);
+    if (code_ != JFNK_OK) { why = err_; return code_; }
+    p2p_ = (agreed == 1);
+    if (!p2p_) p2p_teardown();
     return JFNK_OK;
+  }
+  void p2p_teardown() {
+    for (int q = 0; q < kP2PMaxRanks; ++q) {
+      if (peer_[q] && q != g_.rank) cudaIpcCloseMemHandle(peer_[q]);
+      peer_[q] = nullptr;
+    }
+    if (p2p_block_) { cudaFree(p2p_block_); p2p_block_ = nullptr; }
+    p2p_ = false;
+    cudaGetLastError();
   }
 
  private:
@@ -546,6 +785,15 @@ class CudaOps : public DeviceOps {
   std::string err_;
   const NcclApi* nccl_ = nullptr;
   ncclComm_t comm_ = nullptr;
+  bool capturing_ = false;
+  int64_t capture_launch0_ = 0, graph_replays_ = 0;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  cudaStream_t cap_stream_ = nullptr, user_stream_ = nullptr;
+  bool p2p_ = false;
+  void* p2p_block_ = nullptr;
+  char* peer_[kP2PMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned long long halo_epoch_[kP2PHaloSlots] = {0, 0, 0};
+  unsigned long long reduce_epoch_ = 0;
 };
 
 __global__ void probe_kernel(int* out) { *out = 100; }
@@ -593,5 +841,7 @@ int backend_unique_id(void* id128, std::string& why) {
 int backend_comm_init(DeviceOps* ops, const void* id128, std::string& why) {
   return static_cast<CudaOps*>(ops)->comm_init(id128, why);
 }
+
+int backend_peer_memory(DeviceOps* ops) { return static_cast<CudaOps*>(ops)->peer_memory() ? 1 : 0; }
 
 } // namespace jfnk

@@ -65,11 +65,24 @@ class DeviceOps {
   virtual int status() = 0;
   virtual const char* last_error() const = 0;
 
+  // ---- launch-sequence capture (CUDA graphs) for launch-bound inner loops --------------------------------------
+  // graph_begin(): start recording the operations enqueued from now on instead of running them; returns false when
+  // the backend cannot (then the caller simply keeps enqueuing eagerly).  graph_end_launch(replays): stop recording
+  // and run the recorded sequence `replays` times.  Nothing that synchronises or allocates may be called in between.
+  virtual bool graph_begin() { return false; }
+  virtual void graph_end_launch(int /*replays*/) {}
+
   // ---- scalar arena ---------------------------------------------------------------------------
   virtual void read_scalars(int off, int cnt, double* host) = 0; // synchronises the stream
   virtual void write_scalars(int off, int cnt, const double* host) = 0;
   virtual void allreduce_sum(int off, int cnt) = 0; // across slab ranks; no-op on one rank
   virtual void allreduce_max(int off, int cnt) = 0;
+  // all-reduce (sum) followed by the Hessenberg/Givens step of Arnoldi column j on the reduced values; the CUDA
+  // backend does both in one launch when the ranks share peer memory
+  virtual void allreduce_sum_givens(int off, int cnt, int j, int taken, int rerun) {
+    allreduce_sum(off, cnt);
+    givens(j, taken, rerun);
+  }
 
   // ---- BLAS-1 on slab-local vectors of length grid.n() -------------------------------------------
   // out[i] = V_i . w (i < nv), out[nv] = w . w
@@ -123,6 +136,36 @@ class DeviceOps {
   // F = (u - uval)/dt - (rhs + cn)/2 ; norms as sh_residual (max|t| is max|u|)
   virtual void pma2_combine(const Pma2Params& pp, const double* u, const double* uval, const double* rhs,
                             const double* cn, double* F, int norm_off) = 0;
+  // Whole PMA2 residual / FD-JVP (PMA2_nk.py:121-159) for t = x + a v (v may be null):
+  //   F = (t - uval)/dt - (rhs(t, Laplace(Laplace(t))) + cn)/2
+  //   f0 == null: out = F, xt_out (may be null) = t, norms at S[norm_off..+2] as sh_residual
+  //   f0 != null: out = (F - f0)/div                                   (KrylovJacobian.matvec)
+  // scratch: 4 work vectors.  The CUDA backend runs this as two fused marching passes on large grids
+  // (mesh_march.cuh); the default composes the primitives above.
+  virtual void pma2_eval(const MeshParams& mp, const Pma2Params& pp, const double* const* M, const double* x,
+                         const double* v, ScalarRef a, const double* uval, const double* cn, const double* f0,
+                         ScalarRef div, double* const* scratch, double* xt_out, double* out, int norm_off) {
+    pma2_eval_unfused(mp, pp, M, x, v, a, uval, cn, f0, div, scratch, xt_out, out, norm_off);
+  }
+  void pma2_eval_unfused(const MeshParams& mp, const Pma2Params& pp, const double* const* M, const double* x,
+                         const double* v, ScalarRef a, const double* uval, const double* cn, const double* f0,
+                         ScalarRef div, double* const* scratch, double* xt_out, double* out, int norm_off) {
+    const double* t = x;
+    if (v) {
+      double* tt = (xt_out && !f0) ? xt_out : scratch[3];
+      lincomb(tt, sref(1.0), x, a, v, -1);
+      t = tt;
+    }
+    mesh_laplace(mp, M, t, scratch[0], nullptr, 1, 0);
+    mesh_laplace(mp, M, scratch[0], scratch[1], nullptr, 1, 0);
+    pma2_rhs(pp, t, scratch[1], scratch[2]);
+    if (f0) {
+      pma2_combine(pp, t, uval, scratch[2], cn, scratch[0], norm_off);
+      diff_scale(out, scratch[0], f0, div);
+    } else {
+      pma2_combine(pp, t, uval, scratch[2], cn, out, norm_off);
+    }
+  }
   // droplet: p = -(lap) + PI(h) + Bo cos(alpha2) h
   virtual void droplet_pressure(const DropletParams& dp, const double* h, const double* lap, double* p) = 0;
   // (A, B) = flux components from pressure p and height h  (droplet.py:439-447)

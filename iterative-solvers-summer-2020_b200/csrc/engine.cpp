@@ -214,7 +214,7 @@ int Engine::mesh_relax(double* Q, const double* Uval, double dt, int loops, cons
   const int deriv_bc = (cfg_.problem == JFNK_PROBLEM_DROPLET) ? 1 : 0;
   const double cell = mp_.dksi * mp_.deta;
   double *lap = scratch_[0], *a = scratch_[1], *b = scratch_[2], *t = scratch_[3], *spec = scratch_[4];
-  for (int it = 0; it < loops; ++it) {
+  auto one_pass = [&]() {
     ops_->mesh_metrics(mp_, Q, MF_);
     if (pp.monitor_mode == 0) ops_->mesh_laplace(mp_, MF_, Uval, lap, nullptr, 1, deriv_bc);
     ops_->pma_monitor(pp.monitor_mode, Uval, lap, a);
@@ -225,7 +225,22 @@ int Engine::mesh_relax(double* Q, const double* Uval, double dt, int loops, cons
     ops_->pma_spectral_divide(mp_, pp.gamma, spec);
     ops_->pma_dct2(spec, t, b, 1);
     ops_->lincomb(Q, sref(1.0), Q, sref(dt), b, -1);
+  };
+  // The pass is a fixed sequence of ~14 small launches with no host decision in it, repeated `loops` (400 in
+  // droplet.py:384) times: launch-bound on the reference's grids.  The first pass runs eagerly (it may allocate the DCT
+  // matrices / upload the weight tables); the rest is recorded once and replayed as a CUDA graph.  With an odd number
+  // of smoothing sweeps the ping-pong buffers swap roles every pass, so the recorded unit is two passes.
+  int it = 0;
+  one_pass();
+  it = 1;
+  const int unit = (pp.smoothing_iters % 2 == 0) ? 1 : 2;
+  if (loops - it >= 4 * unit && ops_->graph_begin()) {
+    for (int u = 0; u < unit; ++u) one_pass();
+    const int reps = (loops - it) / unit;
+    ops_->graph_end_launch(reps);
+    it += reps * unit;
   }
+  for (; it < loops; ++it) one_pass();
   metrics_ready_ = false; // Q moved on: the next step must call jfnk_mesh_set_potential (compute_Q_spatial_ders)
   prev_ready_ = false;
   return ops_->status();
@@ -258,10 +273,8 @@ bool Engine::problem_ready(std::string& why) const {
 void Engine::generic_residual(const double* u, double* F, int norm_off) {
   if (cfg_.problem == JFNK_PROBLEM_PMA2) {
     // PMA2_nk.py:121-159
-    ops_->mesh_laplace(mp_, MF_, u, scratch_[0], nullptr, 1, 0);
-    ops_->mesh_laplace(mp_, MF_, scratch_[0], scratch_[1], nullptr, 1, 0);
-    ops_->pma2_rhs(pp_, u, scratch_[1], scratch_[2]);
-    ops_->pma2_combine(pp_, u, UVAL_, scratch_[2], CN_, F, norm_off);
+    ops_->pma2_eval(mp_, pp_, MF_, u, nullptr, sref(1.0), UVAL_, CN_, nullptr, sref(1.0), scratch_.data(), nullptr, F,
+                    norm_off);
   } else {
     // droplet.py:435-450
     ops_->mesh_laplace(mp_, MF_, u, scratch_[0], nullptr, 1, 0);
@@ -276,6 +289,11 @@ int Engine::eval_residual(const double* x, const double* v, ScalarRef a, double*
                           double nrm[3]) {
   if (cfg_.problem == JFNK_PROBLEM_SH) {
     ops_->sh_residual(x, v, a, D_, xt_out, F, norm_off);
+  } else if (cfg_.problem == JFNK_PROBLEM_PMA2) {
+    // t = x + a v is formed inside the evaluation (never stored unless the caller wants the trial iterate)
+    if (!v && xt_out && xt_out != x) ops_->copy(xt_out, x);
+    ops_->pma2_eval(mp_, pp_, MF_, x, v, a, UVAL_, CN_, nullptr, sref(1.0), scratch_.data(), v ? xt_out : nullptr, F,
+                    norm_off);
   } else {
     const double* t = x;
     if (v) {
@@ -329,6 +347,8 @@ void Engine::apply_operator(const double* z, int zn2_idx, double* w, bool unit_i
   ScalarRef div = unit_input ? sref(omega_) : sc;
   if (cfg_.problem == JFNK_PROBLEM_SH) {
     ops_->sh_jvp(x0_, z, sc, div, D_, f0_, w);
+  } else if (cfg_.problem == JFNK_PROBLEM_PMA2) {
+    ops_->pma2_eval(mp_, pp_, MF_, x0_, z, sc, UVAL_, CN_, f0_, div, scratch_.data(), nullptr, w, JS_TMP0 /*unused*/);
   } else {
     ops_->lincomb(scratch_[5], sref(1.0), x0_, sc, z, -1);
     generic_residual(scratch_[5], scratch_[6], JS_TMP0 /*norms unused*/);
@@ -344,16 +364,17 @@ int Engine::jvp(const double* v, double* Jv) {
     return ops_->status();
   }
   if (!x0_) return fail(JFNK_INVALID, "jfnk_jvp: call jfnk_linearize first");
-  // ||v||^2 -> TMP1 ; the operator divides by ||v||, scale back by ||v|| afterwards (0*v when ||v|| == 0)
-  ops_->mdot(0, nullptr, v, JS_TMP1);
-  ops_->allreduce_sum(JS_TMP1, 1);
+  // ||v||^2 -> TMP3 ; the operator divides by ||v||, scale back by ||v|| afterwards (0*v when ||v|| == 0).
+  // (Not TMP0..TMP2: the unfused mesh residuals park their unused norms there before the quotient is formed.)
+  ops_->mdot(0, nullptr, v, JS_TMP3);
+  ops_->allreduce_sum(JS_TMP3, 1);
   double vn2;
-  ops_->read_scalars(JS_TMP1, 1, &vn2);
+  ops_->read_scalars(JS_TMP3, 1, &vn2);
   if (vn2 == 0.0) {
     ops_->lincomb(Jv, sref(0.0), v, sref(0.0), nullptr, -1);
     return ops_->status();
   }
-  apply_operator(v, JS_TMP1, Jv, false);
+  apply_operator(v, JS_TMP3, Jv, false);
   return ops_->status();
 }
 
@@ -397,16 +418,14 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
     double sc[5]; // JS_WW, JS_HN2A, JS_HN2B, JS_RES, JS_FLAGS
     if (!second) {
       ops_->gs_update(j + 1, vs, w, JS_RD, JS_HN2A, single ? j : -1); // single GPU: Givens fused into the last CTA
-      ops_->allreduce_sum(JS_HN2A, 1);
-      if (!single) ops_->givens(j, 0, 0);
+      if (!single) ops_->allreduce_sum_givens(JS_HN2A, 1, j, 0, 0);
       ops_->read_scalars(JS_WW, 5, sc);
       second = (cfg_.gs_mode == JFNK_GS_CGS_IFNEEDED) && (sc[1] < tau2 * sc[0]);
       if (second) {
         ops_->mdot(j + 1, vs, w, JS_RD2);
         ops_->allreduce_sum(JS_RD2, j + 1);
         ops_->gs_update(j + 1, vs, w, JS_RD2, JS_HN2B, -1);
-        ops_->allreduce_sum(JS_HN2B, 1);
-        ops_->givens(j, 1, 1); // redo column j with h = (RD + RD2)/||V||, ||w|| from pass 2
+        ops_->allreduce_sum_givens(JS_HN2B, 1, j, 1, 1); // redo column j with h = (RD + RD2)/||V||, ||w|| from pass 2
         ops_->read_scalars(JS_WW, 5, sc);
       }
     } else {
@@ -415,8 +434,7 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
       ops_->mdot(j + 1, vs, w, JS_RD2);
       ops_->allreduce_sum(JS_RD2, j + 1);
       ops_->gs_update(j + 1, vs, w, JS_RD2, JS_HN2B, -1);
-      ops_->allreduce_sum(JS_HN2B, 1);
-      ops_->givens(j, 1, 0);
+      ops_->allreduce_sum_givens(JS_HN2B, 1, j, 1, 0);
       ops_->read_scalars(JS_WW, 5, sc);
     }
     int st = ops_->status();

@@ -1,0 +1,253 @@
+// Marching kernel for the moving-mesh Laplace_operator (PMA2_nk.py:263-343, droplet.py:601-681) on large grids
+// (config 3: PMA2 on 2048^2), with the PMA2 residual / FD-JVP epilogue fused in.
+//
+// The one-thread-per-point kernels of mesh_kernels.cuh fetch every stencil leg from L1/L2 (~60 loads and ~420
+// instructions per point) and are instruction-issue bound at 2048^2.  Here a CTA owns a strip of 122 interior
+// columns (+3 halo columns per side = 128 threads, one column per thread) and marches down a chunk of rows:
+//   * vertical neighbours live in register windows (7 rows of t, 5 of A22, 5 of g = A12 * D_ksi t);
+//   * horizontal neighbours come from a 5-row shared-memory ring of t and 2-row rings of A11 and f = A12 * D_eta t;
+//   * every field is read from global memory once per point (own column, coalesced), one row ahead of its use;
+//   * the stencil input may be the combination t = x + a v (FD-JVP / line search), formed when a row is loaded.
+// One block barrier per row.  Only interior points (4 <= r < ny-4, 4 <= c < nx-4: no closure stencil in reach) are
+// marched; the frame of 4 rows / columns along each edge is done by a few extra CTAs of the same launch with the
+// general per-point formulas (mesh_laplace_general_g), reading t through the same accessor.
+//
+// Modes: MARCH_LAP        out = Lap t (out2 = t when non-null)
+//        MARCH_PMA2_RESID u = px + pa pv ; F = (u - uval)/dt - (rhs(u, Lap t) + cn)/2 ; out = F ; sum F^2, max|F|, max|u|
+//        MARCH_PMA2_JVP   out = (F - f0)/div
+// Algorithmic bytes per point: LAP 6 fields (t, A11, A22, A12, J in; out) + 1 with v; PMA2 pass 9-11 fields.
+#pragma once
+#include "cuda_common.cuh"
+#include "mesh_kernels.cuh"
+
+namespace jfnk {
+
+// 128 threads x 4 resident CTAs per SM (<= 128 registers): the same 16 warps per SM as 256 x 2, but four row phases
+// in flight instead of two, which hides more of the per-row barrier + fp64 dependency latency (measured at 2048^2:
+// 87 vs 93 us per pass; 256 x 3 and 128 x 6 with the register cap at 80 spill and are slower).
+#ifndef JFNK_MARCH_THREADS
+#define JFNK_MARCH_THREADS 128
+#endif
+#ifndef JFNK_MARCH_MINCTAS
+#define JFNK_MARCH_MINCTAS 4
+#endif
+constexpr int kMarchThreads = JFNK_MARCH_THREADS;
+constexpr int kMarchHalo = 3;
+constexpr int kMarchOut = kMarchThreads - 2 * kMarchHalo; // output columns per strip
+constexpr int kMarchRing = 8;                             // rows of t kept in shared memory (5 live; power of 2)
+constexpr int kMarchPad = 4;                              // slack columns so that halo threads index in range
+constexpr int kMarchMinRows = 8;                          // rows per chunk at least (6 warm-up rows per chunk)
+
+enum MarchMode { MARCH_LAP = 0, MARCH_PMA2_RESID = 1, MARCH_PMA2_JVP = 2 };
+
+struct MarchArgs {
+  MeshGeom gm;
+  MetricCPtrs M;
+  const double *x, *v;   // stencil input t = x + a v (v null: t = x)
+  ScalarRef a;
+  const double *px, *pv; // pointwise u = px + pa pv (PMA2 modes; pv may be null)
+  ScalarRef pa;
+  const double *uval, *cn, *f0;
+  ScalarRef div;
+  Pma2Params pp;
+  double *out, *out2;
+  int norm_off, deriv_bc;
+  int rows_per_chunk, nstrips, nframe_ctas;
+  int debug_skip; // profiling aid (JFNK_MARCH_DEBUG): 1 = frame CTAs idle, 2 = interior CTAs idle; results are then wrong
+};
+
+template <int MODE, bool HAS_V>
+__global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_kernel(const __grid_constant__ MarchArgs A, double* S,
+                                                                       ReduceWs ws) {
+  constexpr int W = kMarchThreads + 2 * kMarchPad;
+  __shared__ double Ts[kMarchRing][W];
+  __shared__ double A11s[2][W];
+  __shared__ double Fs[2][W];
+  const MeshGeom& g = A.gm;
+  const int nx = g.nx, ny = g.ny;
+  const int tid = threadIdx.x;
+  const double a = HAS_V ? eval_sref(S, A.a) : 0.0;
+  const bool has_pv = (MODE != MARCH_LAP) && A.pv != nullptr;
+  const double pa = has_pv ? eval_sref(S, A.pa) : 0.0;
+  const double inv_dv = (MODE == MARCH_PMA2_JVP) ? __drcp_rn(eval_sref(S, A.div)) : 1.0;
+  const double inv_dt = (MODE != MARCH_LAP) ? __drcp_rn(A.pp.dt) : 1.0;
+  double acc[3] = {0.0, 0.0, 0.0};
+
+  // result of one point: tc = stencil input at the point, lap = Lap t, (u, uval, cn, f0) = pointwise operands
+  auto emit = [&](size_t e, bool bdy, double tc, double lap, double u, double uval, double cn, double f0) {
+    if (MODE == MARCH_LAP) {
+      A.out[e] = lap;
+      if (A.out2) A.out2[e] = tc;
+    } else {
+      double rhs = bdy ? 0.0 : pma2_rhs_point(A.pp, u, lap);
+      double F = (u - uval) * inv_dt - (rhs + cn) * 0.5; // pma2_combine_point with 1/dt rounded once
+      if (MODE == MARCH_PMA2_RESID) {
+        A.out[e] = F;
+        acc[0] = fma(F, F, acc[0]); acc[1] = fmax(acc[1], fabs(F)); acc[2] = fmax(acc[2], fabs(u));
+      } else {
+        A.out[e] = (F - f0) * inv_dv;
+      }
+    }
+  };
+
+  if ((int)blockIdx.x < A.nframe_ctas) {
+    if (A.debug_skip == 1) return;
+    // ---- frame: rows 0..3, ny-4..ny-1 (8 nx points), then columns 0..3, nx-4..nx-1 of the remaining rows ----
+    const long long nrowpts = 8LL * nx, nf = nrowpts + 8LL * (ny - 8);
+    auto tf = [&](int r, int c) -> double {
+      size_t e = (size_t)r * nx + c;
+      double xv = A.x[e];
+      if (HAS_V) xv = combine(xv, a, A.v[e]);
+      return xv;
+    };
+    for (long long i = (long long)blockIdx.x * kMarchThreads + tid; i < nf; i += (long long)A.nframe_ctas * kMarchThreads) {
+      int r, c;
+      if (i < nrowpts) {
+        int fr = (int)(i / nx);
+        r = fr < 4 ? fr : ny - 8 + fr;
+        c = (int)(i - (long long)fr * nx);
+      } else {
+        long long k = i - nrowpts;
+        int cc = (int)(k & 7);
+        r = 4 + (int)(k >> 3);
+        c = cc < 4 ? cc : nx - 8 + cc;
+      }
+      double xx, yy;
+      mesh_laplace_general_g(g, A.M.m, tf, r, c, A.deriv_bc, xx, yy);
+      const size_t e = (size_t)r * nx + c;
+      const bool bdy = (r == 0 || c == 0 || r == ny - 1 || c == nx - 1);
+      double u = 0.0, uval = 0.0, cn = 0.0, f0 = 0.0;
+      if (MODE != MARCH_LAP) {
+        u = A.px[e];
+        if (has_pv) u = combine(u, pa, A.pv[e]);
+        uval = A.uval[e]; cn = A.cn[e];
+        if (MODE == MARCH_PMA2_JVP) f0 = A.f0[e];
+      }
+      emit(e, bdy, MODE == MARCH_LAP ? tf(r, c) : 0.0, xx + yy, u, uval, cn, f0);
+    }
+  } else {
+    // ---- interior: march down rows [r0, r1) of one strip ----
+    if (A.debug_skip == 2) return;
+    const int id = (int)blockIdx.x - A.nframe_ctas;
+    const int strip = id % A.nstrips, chunk = id / A.nstrips;
+    const int r0 = 4 + chunk * A.rows_per_chunk;
+    const int r1 = min(ny - 4, r0 + A.rows_per_chunk);
+    const int c_raw = 4 + strip * kMarchOut - kMarchHalo + tid;
+    const int c = min(c_raw, nx - 1); // threads past the right edge load a valid column and compute nothing
+    const bool is_out = tid >= kMarchHalo && tid < kMarchHalo + kMarchOut && c_raw < nx - 4;
+    const int st = tid + kMarchPad;
+    const double* __restrict__ Jp = A.M.m[3];
+    const double* __restrict__ A11p = A.M.m[4];
+    const double* __restrict__ A22p = A.M.m[5];
+    const double* __restrict__ A12p = A.M.m[6];
+    const double wx0 = g.c1x[0], wx1 = g.c1x[1], wx3 = g.c1x[3], wx4 = g.c1x[4];
+    const double wy0 = g.c1y[0], wy1 = g.c1y[1], wy3 = g.c1y[3], wy4 = g.c1y[4];
+    // (the centred first-derivative weight of the point itself is 0 and is left out of the sums)
+
+    // Register windows as circular buffers of period 7 (the row loop is unrolled 7x, so every index below is a
+    // compile-time constant and no register is ever moved): with m counted from the first warm-up row,
+    //   tw[m % 7]           = t(r0 - 3 + m, c)   rows r-3..r+3 of output row r = r0 + u are slots (u + k + 3) % 7
+    //   a22w[m % 7], gw[..] = A22, g (r0 - 2 + m, c)   rows r-2..r+2 are slots (u + k + 2) % 7
+    double tw[7], a22w[7], gw[7];
+    const double rx = __drcp_rn(288 * g.dksi2), ry = __drcp_rn(288 * g.deta2); // one rounding each, instead of a
+                                                                              // division per point and direction
+
+    // warm-up: rows r0-3 .. r0+2 of t ; g and A22 of rows r0-2 .. r0+1
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+      const int rho = r0 - 3 + m;
+      const size_t off = (size_t)rho * nx + c;
+      double tv = __ldg(A.x + off);
+      if (HAS_V) tv = combine(tv, a, __ldg(A.v + off));
+      tw[m] = tv;
+      Ts[rho & (kMarchRing - 1)][st] = tv;
+      __syncthreads();
+      if (m >= 1 && m <= 4) {
+        const double* T = Ts[rho & (kMarchRing - 1)] + st;
+        const double vk = wx0 * T[-2] + wx1 * T[-1] + wx3 * T[1] + wx4 * T[2];
+        gw[m - 1] = __ldg(A12p + off) * vk;
+        a22w[m - 1] = __ldg(A22p + off);
+      }
+    }
+
+    // software pipeline: the operands of iteration r are loaded during iteration r-1
+    double n_x, n_v = 0.0, n_a12r, n_a12, n_a22, n_a11, n_J;
+    auto prefetch = [&](int r) {
+      const size_t o3 = (size_t)(r + 3) * nx + c, o2 = (size_t)(r + 2) * nx + c, o0 = (size_t)r * nx + c;
+      n_x = __ldg(A.x + o3);
+      if (HAS_V) n_v = __ldg(A.v + o3);
+      n_a12 = __ldg(A12p + o2);
+      n_a22 = __ldg(A22p + o2);
+      n_a12r = __ldg(A12p + o0); // second touch of this element (first: two rows ago): an L1/L2 hit, saves a window
+      n_a11 = __ldg(A11p + o0);
+      n_J = __ldg(Jp + o0);
+    };
+    prefetch(r0);
+    for (int rb = r0; rb < r1; rb += 7) {
+#pragma unroll
+      for (int u = 0; u < 7; ++u) {
+        const int r = rb + u;
+        if (r >= r1) break;
+        // take the prefetched row
+        const double tnew = HAS_V ? combine(n_x, a, n_v) : n_x;
+        tw[(u + 6) % 7] = tnew;
+        a22w[(u + 4) % 7] = n_a22;
+        const double a12r2 = n_a12, a12r = n_a12r, a11 = n_a11, Jv = n_J;
+        if (r + 1 < r1) prefetch(r + 1);
+        // pointwise operands of this row: issued here, consumed after the barrier
+        double uu = 0.0, pvv = 0.0, uval = 0.0, cn = 0.0, f0 = 0.0;
+        if (MODE != MARCH_LAP) {
+          const size_t o0 = (size_t)r * nx + c;
+          uu = __ldg(A.px + o0);
+          if (has_pv) pvv = __ldg(A.pv + o0);
+          uval = __ldg(A.uval + o0);
+          cn = __ldg(A.cn + o0);
+          if (MODE == MARCH_PMA2_JVP) f0 = __ldg(A.f0 + o0);
+        }
+
+        const int slot = r & 1;
+        Ts[(r + 3) & (kMarchRing - 1)][st] = tnew;
+        A11s[slot][st] = a11;
+#define TW(k) tw[(u + (k) + 3) % 7]
+#define AY(k) a22w[(u + (k) + 2) % 7]
+#define GW(k) gw[(u + (k) + 2) % 7]
+        // D_eta t at (r, c) from the register window ; f = A12 D_eta t
+        const double ve = wy0 * TW(-2) + wy1 * TW(-1) + wy3 * TW(1) + wy4 * TW(2);
+        Fs[slot][st] = a12r * ve;
+        {
+          // D_ksi t at (r+2, c) from the row staged one iteration ago ; g = A12 D_ksi t
+          const double* T2 = Ts[(r + 2) & (kMarchRing - 1)] + st;
+          const double vk = wx0 * T2[-2] + wx1 * T2[-1] + wx3 * T2[1] + wx4 * T2[2];
+          GW(2) = a12r2 * vk;
+        }
+        __syncthreads();
+        if (is_out) {
+          const double* T = Ts[r & (kMarchRing - 1)] + st;
+          const double* AX = A11s[slot] + st;
+          const double* FX = Fs[slot] + st;
+          const double xx = (4 * (AX[-1] * (T[-3] - 8 * T[-2] + 8 * T[0] - T[1])) -
+                             (-AX[-2] + 9 * AX[-1] + 9 * AX[0] - AX[1]) * (T[-2] - 27 * T[-1] + 27 * T[0] - T[1]) +
+                             (-AX[-1] + 9 * AX[0] + 9 * AX[1] - AX[2]) * (T[-1] - 27 * T[0] + 27 * T[1] - T[2]) -
+                             4 * (AX[1] * (T[-1] - 8 * T[0] + 8 * T[2] - T[3]))) * rx;
+          const double yy = (4 * (AY(-1) * (TW(-3) - 8 * TW(-2) + 8 * TW(0) - TW(1))) -
+                             (-AY(-2) + 9 * AY(-1) + 9 * AY(0) - AY(1)) * (TW(-2) - 27 * TW(-1) + 27 * TW(0) - TW(1)) +
+                             (-AY(-1) + 9 * AY(0) + 9 * AY(1) - AY(2)) * (TW(-1) - 27 * TW(0) + 27 * TW(1) - TW(2)) -
+                             4 * (AY(1) * (TW(-1) - 8 * TW(0) + 8 * TW(2) - TW(3)))) * ry;
+          double accx = 0.0, accy = 0.0;
+          accx += wx0 * FX[-2]; accx += wx1 * FX[-1]; accx += wx3 * FX[1]; accx += wx4 * FX[2];
+          accy += wy0 * GW(-2); accy += wy1 * GW(-1); accy += wy3 * GW(1); accy += wy4 * GW(2);
+          const double rJ = __drcp_rn(Jv);
+          const double lap = (xx + accx) * rJ + (yy + accy) * rJ;
+          if (has_pv) uu = combine(uu, pa, pvv);
+          emit((size_t)r * nx + c, false, TW(0), lap, uu, uval, cn, f0);
+        }
+#undef TW
+#undef AY
+#undef GW
+      }
+    }
+  }
+  if (MODE == MARCH_PMA2_RESID) grid_reduce<3>(acc, 0x6u, ws, S + A.norm_off);
+}
+
+} // namespace jfnk

@@ -125,10 +125,11 @@ JF_HD void mesh_metrics_point(const MeshGeom& g, const double* Q, int r, int c, 
 }
 
 // ---- Laplace_operator (PMA2_nk.py:263-343, droplet.py:601-681) ---------------------------------
-// conservative (A v')' along one grid line: A, v sampled at stride `st`, i = index along the line, n = line length
-JF_HD double cons_line(const double* A, const double* v, size_t st, int i, int n, double h2) {
-#define A_(k) A[(size_t)(k) * st]
-#define V_(k) v[(size_t)(k) * st]
+// conservative (A v')' along one grid line.  A_(k), V_(k): coefficient and field at index k of the line, i = index of
+// the output point along the line, n = line length.  The accessors let the same rows be applied to a field that only
+// exists as a combination x + a v (fused FD-JVP) as well as to a plain array.
+template <class FA, class FV>
+JF_HD double cons_line_g(FA A_, FV V_, int i, int n, double h2) {
   if (i == 0 || i == n - 1) return 0.0; // boundary columns stay 0
   if (i == 1)
     return A_(1) * (10 * V_(0) - 15 * V_(1) - 4 * V_(2) + 14 * V_(3) - 6 * V_(4) + V_(5)) / (12 * h2) +
@@ -150,19 +151,24 @@ JF_HD double cons_line(const double* A, const double* v, size_t st, int i, int n
           (-A_(i - 1) + 9 * A_(i) + 9 * A_(i + 1) - A_(i + 2)) * (V_(i - 1) - 27 * V_(i) + 27 * V_(i + 1) - V_(i + 2)) -
           4 * (A_(i + 1) * (V_(i - 1) - 8 * V_(i) + 8 * V_(i + 2) - V_(i + 3)))) /
          (288 * h2);
-#undef A_
-#undef V_
+}
+// plain arrays: A, v sampled at stride `st`
+JF_HD double cons_line(const double* A, const double* v, size_t st, int i, int n, double h2) {
+  return cons_line_g([=](int k) { return A[(size_t)k * st]; }, [=](int k) { return v[(size_t)k * st]; }, i, n, h2);
 }
 
-// first derivatives of v as Laplace_operator's callers pass them in.  deriv_bc = 1 reproduces
-// compute_u_spatial_ders of droplet.py:719-722 (incl. its `U_dksi[Ibdy.Bottom] = 0` line).
-JF_HD double v_ksi_bc(const MeshGeom& g, const double* v, int r, int c, int deriv_bc) {
-  if (deriv_bc && (c == 0 || c == g.nx - 1 || r == 0)) return 0.0;
-  return d_ksi(g, v, r, c);
+// first derivatives of a field given by an accessor f(row, col)
+template <class F>
+JF_HD double d_ksi_g(const MeshGeom& g, F f, int r, int c) {
+  int t = fd_type(c, g.nx), s = d1_start(c, g.nx, t);
+  const double* w = g.tab->d1x + t * 5;
+  return w[0] * f(r, s) + w[1] * f(r, s + 1) + w[2] * f(r, s + 2) + w[3] * f(r, s + 3) + w[4] * f(r, s + 4);
 }
-JF_HD double v_eta_bc(const MeshGeom& g, const double* v, int r, int c, int deriv_bc) {
-  if (deriv_bc && r == g.ny - 1) return 0.0;
-  return d_eta(g, v, r, c);
+template <class F>
+JF_HD double d_eta_g(const MeshGeom& g, F f, int r, int c) {
+  int t = fd_type(r, g.ny), s = d1_start(r, g.ny, t);
+  const double* w = g.tab->d1y + t * 5;
+  return w[0] * f(s, c) + w[1] * f(s + 1, c) + w[2] * f(s + 2, c) + w[3] * f(s + 3, c) + w[4] * f(s + 4, c);
 }
 
 // Interior fast path of Laplace_operator: every stencil involved is the centred one (no closure rows/columns within
@@ -219,20 +225,22 @@ JF_UNROLL
   vyy = (yy + accy) / Jv;
 }
 
-JF_HD void mesh_laplace_point(const MeshGeom& g, const double* const* M, const double* v, int r, int c, int deriv_bc,
-                              double& vxx, double& vyy) {
-  if (r >= 4 && r < g.ny - 4 && c >= 4 && c < g.nx - 4) { // no closure stencil within reach
-    mesh_laplace_interior(g, M, v, r, c, vxx, vyy);
-    return;
-  }
+// General path of Laplace_operator for a field given by an accessor f(row, col): closure rows / columns selected per
+// point.  The first derivatives of v fed to the cross terms are what Laplace_operator's callers pass in: deriv_bc = 1
+// reproduces compute_u_spatial_ders of droplet.py:719-722 (v_ksi = 0 on the left/right/bottom edges -- incl. its
+// `U_dksi[Ibdy.Bottom] = 0` line -- and v_eta = 0 on the top edge).
+template <class F>
+JF_HD void mesh_laplace_general_g(const MeshGeom& g, const double* const* M, F f, int r, int c, int deriv_bc, double& vxx,
+                                  double& vyy) {
   const double* J = M[3];
-  const double* A11 = M[4];
-  const double* A22 = M[5];
+  const double* A11 = M[4] + (size_t)r * g.nx;
+  const double* A22 = M[5] + c;
   const double* A12 = M[6];
+  const size_t nx = g.nx;
   size_t e = (size_t)r * g.nx + c;
   // B.1: (A11 v_ksi)_ksi along the row, (A22 v_eta)_eta along the column
-  double xx = cons_line(A11 + (size_t)r * g.nx, v + (size_t)r * g.nx, 1, c, g.nx, g.dksi2);
-  double yy = cons_line(A22 + c, v + c, (size_t)g.nx, r, g.ny, g.deta2);
+  double xx = cons_line_g([=](int k) { return A11[k]; }, [=](int k) { return f(r, k); }, c, g.nx, g.dksi2);
+  double yy = cons_line_g([=](int k) { return A22[(size_t)k * nx]; }, [=](int k) { return f(k, c); }, r, g.ny, g.deta2);
   // B.2: D_ksi(A12 v_eta) with left/right columns zeroed ; D_eta(A12 v_ksi) with top/bottom rows zeroed
   if (c != 0 && c != g.nx - 1) {
     int t = fd_type(c, g.nx), s = d1_start(c, g.nx, t);
@@ -241,7 +249,8 @@ JF_HD void mesh_laplace_point(const MeshGeom& g, const double* const* M, const d
     for (int k = 0; k < 5; ++k) {
       if (w[k] == 0.0) continue;
       int cc = s + k;
-      acc += w[k] * (A12[(size_t)r * g.nx + cc] * v_eta_bc(g, v, r, cc, deriv_bc));
+      double ve = (deriv_bc && r == g.ny - 1) ? 0.0 : d_eta_g(g, f, r, cc);
+      acc += w[k] * (A12[(size_t)r * g.nx + cc] * ve);
     }
     xx += acc;
   }
@@ -252,12 +261,23 @@ JF_HD void mesh_laplace_point(const MeshGeom& g, const double* const* M, const d
     for (int k = 0; k < 5; ++k) {
       if (w[k] == 0.0) continue;
       int rr = s + k;
-      acc += w[k] * (A12[(size_t)rr * g.nx + c] * v_ksi_bc(g, v, rr, c, deriv_bc));
+      double vk = (deriv_bc && (c == 0 || c == g.nx - 1 || rr == 0)) ? 0.0 : d_ksi_g(g, f, rr, c);
+      acc += w[k] * (A12[(size_t)rr * g.nx + c] * vk);
     }
     yy += acc;
   }
   vxx = xx / J[e];
   vyy = yy / J[e];
+}
+
+JF_HD void mesh_laplace_point(const MeshGeom& g, const double* const* M, const double* v, int r, int c, int deriv_bc,
+                              double& vxx, double& vyy) {
+  if (r >= 4 && r < g.ny - 4 && c >= 4 && c < g.nx - 4) { // no closure stencil within reach
+    mesh_laplace_interior(g, M, v, r, c, vxx, vyy);
+    return;
+  }
+  const size_t nx = g.nx;
+  mesh_laplace_general_g(g, M, [=](int rr, int cc) { return v[(size_t)rr * nx + cc]; }, r, c, deriv_bc, vxx, vyy);
 }
 
 // ---- PMA2 pointwise (PMA2_nk.py:131,139,157-159 ; :410-418) -------------------------------------

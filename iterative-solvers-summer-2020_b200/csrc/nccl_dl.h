@@ -14,6 +14,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t);
   const char* (*GetErrorString)(ncclResult_t);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*GroupStart)();
@@ -40,6 +41,7 @@ inline const NcclApi* nccl_api(std::string& why) {
       api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
       api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
       api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+      api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
       api.Send = (decltype(api.Send))sym("ncclSend");
       api.Recv = (decltype(api.Recv))sym("ncclRecv");
       api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");

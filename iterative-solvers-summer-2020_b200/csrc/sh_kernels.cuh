@@ -47,9 +47,6 @@ __device__ __forceinline__ const double* sh_row(const double* base, const double
   return base + (size_t)r * nx;
 }
 
-// x + a*v exactly as NumPy evaluates `x0 + sc*v` (product rounded, then sum rounded)
-__device__ __forceinline__ double combine(double x, double a, double v) { return __dadd_rn(x, __dmul_rn(a, v)); }
-
 struct ShAcc {
   double f2, fmax, xmax;
 };

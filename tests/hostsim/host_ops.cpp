@@ -395,6 +395,7 @@ DeviceOps* backend_make_ops(const jfnk_config& cfg, std::string&, int&) {
 }
 int backend_unique_id(void* id128, std::string&) { memset(id128, 0, 128); return JFNK_OK; }
 int backend_comm_init(DeviceOps*, const void*, std::string&) { return JFNK_OK; }
+int backend_peer_memory(DeviceOps*) { return 0; }
 
 } // namespace jfnk
 

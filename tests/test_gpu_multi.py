@@ -33,7 +33,7 @@ WORKER = textwrap.dedent("""
     full = comm.gather_rows(U, N, N)
     fully = comm.gather_rows(y, N, N)
     if comm.rank == 0:
-        np.savez({out!r}, U=full, Lu=fully, nit=[h["nit"] for h in hist])
+        np.savez({out!r}, U=full, Lu=fully, nit=[h["nit"] for h in hist], peer=int(F.context().peer_memory()))
     dist.destroy_process_group()
 """)
 
@@ -46,8 +46,10 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("N,variant", [(64, 1), (512, 0)])
-def test_nccl_slab_solver_matches_single_gpu_and_oracle(tmp_path, N, variant):
+@pytest.mark.parametrize("N,variant,p2p", [(64, 1, 1), (512, 0, 1), (512, 0, 0)])
+def test_nccl_slab_solver_matches_single_gpu_and_oracle(tmp_path, N, variant, p2p):
+    """p2p=1: halos pushed into the neighbours' buffers over NVLink + one-shot peer-memory all-reduce (the product
+    path on one node); p2p=0: JFNK_P2P=0 forces the NCCL send/recv + ncclAllReduce path (the fallback)."""
     import torch
 
     ngpu = torch.cuda.device_count()
@@ -63,9 +65,11 @@ def test_nccl_slab_solver_matches_single_gpu_and_oracle(tmp_path, N, variant):
     script.write_text(WORKER.format(root=ROOT, N=N, nsteps=nsteps, out=out, variant=variant))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    env = dict(os.environ, JFNK_P2P=str(p2p))
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-4000:]
     multi = np.load(out)
+    assert int(multi["peer"]) == p2p, "peer-memory path was expected to be %s" % ("active" if p2p else "off")
     U0 = jf.seeded_slab_state(N, 0, N, seed=1234)
     o = SHOracle(N=N, d=0.625 * N)
     assert np.abs(multi["Lu"] - o.L @ U0).max() / np.abs(o.L @ U0).max() < 1e-14

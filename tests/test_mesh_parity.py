@@ -37,6 +37,31 @@ def test_pma2_operators_and_residual_vs_reference_golden(buffers):
     assert F.last_history["nit"] == len(g["op_hist"])
 
 
+def test_mesh_jvp_matches_krylov_jacobian_matvec(buffers):
+    """KrylovJacobian.matvec (scipy/optimize/_nonlin.py:1557-1565) on the moving-mesh residual:
+    (F(x0 + sc v) - F(x0))/sc with sc = omega/||v||, omega = rdiff max(1,|x0|_inf)/max(1,|F(x0)|_inf), at the script's
+    initial state (U = 0 on the uniform mesh, PMA2_nk.py:68-71) where F = O(1) and omega ~ 1e-8.  Both sides are FD
+    quotients: they agree to rounding(F)/sc, ~1e-9 relative here (tolerance 1e-6)."""
+    N = 51
+    xi = np.linspace(-1, 1, N)
+    X, Y = np.meshgrid(xi, xi)
+    Q = (0.5 * X ** 2 + 0.5 * Y ** 2).reshape(-1)
+    x0 = np.zeros(N * N)
+    o = PMA2Oracle(N=N)
+    o.set_mesh(Q)
+    o.set_prev(x0)
+    F = jf.PMA2Residual(N=N, buffers=buffers)
+    F.set_mesh(Q)
+    F.set_prev(x0)
+    v = (np.sin(2 * X) * np.cos(Y) * (1 - X ** 2) * (1 - Y ** 2)).reshape(-1)
+    f0 = o.residual(x0)
+    omega = np.sqrt(np.finfo(float).eps) * max(1.0, np.abs(x0).max()) / max(1.0, np.abs(f0).max())
+    sc = omega / np.linalg.norm(v)
+    ref = (o.residual(x0 + sc * v) - f0) / sc
+    F.linearize(x0)
+    assert relmax(F.jvp(v), ref) < 1e-6
+
+
 def test_pma2_time_loop_vs_reference_golden(buffers):
     """PMA2_nk.py main() loop (:80-106): device Newton-Krylov per step; the mesh update (DCT PMA solve) is the
     'next' component of SURVEY.md section 8f and runs on the host oracle, feeding Q to the engine each step."""
@@ -146,3 +171,82 @@ def test_mesh_argument_errors(buffers):
         F.set_prev(np.zeros(51 * 51))  # mesh potential not set
     with pytest.raises(ValueError):
         jf.PMA2Residual(N=5, buffers=buffers).context()
+
+
+# ---- marching Laplace kernel (mesh_march.cuh): the large-grid path of config 3 ---------------------------------
+def _pma2_state(N, seed=3):
+    """smooth non-trivial mesh potential and solution on the N x N grid (metric J stays positive)"""
+    xi = np.linspace(-1, 1, N)
+    X, Y = np.meshgrid(xi, xi)
+    # (a small perturbation: a larger one drives Q_etaeta -> 0 on the top edge, where A22 = Q_ksiksi/Q_etaeta then
+    #  amplifies the rounding of the 1/h^2 boundary closure by 1e4 and no two fp64 evaluations agree to 1e-9)
+    Q = 0.5 * X ** 2 + 0.5 * Y ** 2 + 0.002 * np.cos(2.1 * X + 0.3) * np.sin(1.7 * Y - 0.2)
+    rng = np.random.default_rng(seed)
+    u = 0.05 * np.sin(3 * X + 1) * np.cos(2 * Y) + 1e-3 * rng.standard_normal((N, N))
+    u0 = 0.04 * np.cos(2 * X) * np.cos(3 * Y + 0.5)
+    return Q.reshape(-1), u.reshape(-1), u0.reshape(-1)
+
+
+@pytest.mark.gpu
+def test_pma2_marching_kernel_small_grid_vs_reference_golden(cuda_buffers):
+    """kernel_variant=2 forces the marching kernel on the reference's own 51 x 51 grid: same goldens as above."""
+    g = np.load(os.path.join(GOLD, "pma2_n51.npz"))
+    F = jf.PMA2Residual(N=51, buffers=cuda_buffers, kernel_variant=2)
+    F.set_mesh(g["op_Q"])
+    F.set_prev(g["op_Uval"])
+    assert relmax(F(g["op_u"]), g["op_residual"]) < 1e-10
+    U = jf.newton_krylov(F, g["op_Uval"], verbose=0)
+    assert rel(U, g["op_Unew"]) < 1e-8
+    assert F.last_history["nit"] == len(g["op_hist"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [300, 523])
+def test_pma2_marching_kernel_vs_point_kernel_and_oracle(cuda_buffers, N):
+    """Default rule (marching kernel from 256^2 points up: 2 and 3 strips of 250 columns, several row chunks) against
+    the one-thread-per-point kernels (kernel_variant=1) and against the oracle's sparse-matrix residual."""
+    Q, u, u0 = _pma2_state(N)
+    dt = 1e-4 * ((2.0 / (N - 1)) / 0.04) ** 4
+    Fm = jf.PMA2Residual(N=N, dt=dt, buffers=cuda_buffers)
+    Fp = jf.PMA2Residual(N=N, dt=dt, buffers=cuda_buffers, kernel_variant=1)
+    for F in (Fm, Fp):
+        F.set_mesh(Q)
+        F.set_prev(u0)
+    rm, rp = Fm(u), Fp(u)
+    assert relmax(rm, rp) < 1e-13  # same formulas, same order: only FMA contraction may differ
+    o = PMA2Oracle(N=N, k=dt)
+    o.set_mesh(Q)
+    o.set_prev(u0)
+    # summation-order / FMA differences are amplified by the two 1/h^2 Laplacians: measured 7e-11 against the
+    # reference's goldens at N = 51, growing like (N/51)^4
+    assert relmax(rm, o.residual(u)) < 2e-10 * (N / 51.0) ** 4
+    # FD-JVP at the same linearisation point.  Linearised at U = 0 (the script's initial state), where F = O(1) and
+    # omega ~ 1e-8: at the rough state above |F|_inf ~ 1e9 drives omega to ~1e-17 and the quotient is rounding noise
+    # in any implementation.  Both kernels then agree to rounding(F)/sc.
+    zero = np.zeros(N * N)
+    xi = np.linspace(-1, 1, N)
+    X, Y = np.meshgrid(xi, xi)
+    v = (np.sin(2 * X) * np.cos(Y) + 1e-6 * np.random.default_rng(5).standard_normal((N, N))).reshape(-1)
+    for F in (Fm, Fp):
+        F.set_prev(zero)
+        F.linearize(zero)
+    jm, jp = Fm.jvp(v), Fp.jvp(v)
+    assert relmax(jm, jp) < 1e-6
+    # line-search form t = x + s dx with the trial iterate kept, through Newton-Krylov: same converged field
+    Um = jf.newton_krylov(Fm, zero, verbose=0)
+    Up = jf.newton_krylov(Fp, zero, verbose=0)
+    assert rel(Um, Up) < 1e-8
+    assert Fm.last_history["nit"] == Fp.last_history["nit"]
+
+
+@pytest.mark.gpu
+def test_droplet_marching_laplace_rectangular_grid(cuda_buffers):
+    """MARCH_LAP with deriv_bc=1 on the 91 x 61 droplet grid (set_prev and the mesh relaxation use the summed
+    Laplace_operator): goldens of the reference's own modules."""
+    g = np.load(os.path.join(GOLD, "droplet_91x61.npz"))
+    F = jf.DropletResidual(buffers=cuda_buffers, kernel_variant=2)
+    F.set_mesh(g["state_Q"])
+    F.set_prev(g["state_U"], 1e-4)
+    assert relmax(F(g["op_u"]), g["op_residual"]) < 1e-10
+    Q400 = F.relax_mesh(g["state_Q"], g["state_U"], 3e-9, loops=400)
+    assert rel(Q400 - g["state_Q"], g["run_Q0"] - g["state_Q"]) < 1e-10
