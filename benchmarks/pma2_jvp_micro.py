@@ -1,5 +1,10 @@
+"""Micro-benchmark of the fused PMA2 FD-JVP (two passes of the marching Laplace kernel, mesh_march.cuh) on an N x N grid:
+device time per launch from the engine's CUDA-event profile and algorithmic GB/s (7 + 11 fields of 8 B per point).
+
+    python benchmarks/pma2_jvp_micro.py [N]            # JFNK_MARCH_DEBUG=1|2 idles the frame / interior CTAs
+"""
 import sys, os, json
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import jfnk_b200 as jf
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2048

@@ -510,10 +510,13 @@ class CudaOps : public DeviceOps {
   template <int MODE, bool HAS_V>
   void march_launch(MarchArgs& A, const MeshParams& mp, double vecs) {
     A.gm = geom(mp);
+    constexpr size_t smem = march_smem_bytes(MODE);
     int& per_sm = occupancy_[reinterpret_cast<const void*>(mesh_march_kernel<MODE, HAS_V>)];
     if (per_sm == 0) {
+      ck(cudaFuncSetAttribute(mesh_march_kernel<MODE, HAS_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+         "cudaFuncSetAttribute(march smem)");
       int nb_ = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, mesh_march_kernel<MODE, HAS_V>, kMarchThreads, 0) != cudaSuccess || nb_ < 1) nb_ = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, mesh_march_kernel<MODE, HAS_V>, kMarchThreads, smem) != cudaSuccess || nb_ < 1) nb_ = 1;
       per_sm = nb_;
     }
     // all CTAs resident at once: a few frame CTAs (general per-point path) + strips x row chunks of the interior
@@ -528,7 +531,7 @@ class CudaOps : public DeviceOps {
     static const int dbg = getenv("JFNK_MARCH_DEBUG") ? atoi(getenv("JFNK_MARCH_DEBUG")) : 0;
     A.debug_skip = (MODE == MARCH_PMA2_RESID) ? 0 : dbg; // (the reduction of RESID needs every CTA)
     Prof prof(this, K_MESH, nb(vecs));
-    mesh_march_kernel<MODE, HAS_V><<<A.nframe_ctas + A.nstrips * nchunks, kMarchThreads, 0, stream_>>>(A, S_, ws_);
+    mesh_march_kernel<MODE, HAS_V><<<A.nframe_ctas + A.nstrips * nchunks, kMarchThreads, smem, stream_>>>(A, S_, ws_);
   }
   MarchArgs march_args(const double* const* M, const double* x, const double* v, ScalarRef a, double* out) {
     MarchArgs A;

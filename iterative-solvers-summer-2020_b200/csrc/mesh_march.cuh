@@ -4,18 +4,25 @@
 // The one-thread-per-point kernels of mesh_kernels.cuh fetch every stencil leg from L1/L2 (~60 loads and ~420
 // instructions per point) and are instruction-issue bound at 2048^2.  Here a CTA owns a strip of 122 interior
 // columns (+3 halo columns per side = 128 threads, one column per thread) and marches down a chunk of rows:
-//   * vertical neighbours live in register windows (7 rows of t, 5 of A22, 5 of g = A12 * D_ksi t);
-//   * horizontal neighbours come from a 5-row shared-memory ring of t and 2-row rings of A11 and f = A12 * D_eta t;
-//   * every field is read from global memory once per point (own column, coalesced), one row ahead of its use;
-//   * the stencil input may be the combination t = x + a v (FD-JVP / line search), formed when a row is loaded.
+//   * vertical neighbours live in register windows (7 rows of t, 5 of A22, 5 of g = A12 * D_ksi t), held as circular
+//     buffers whose indices are compile-time constants because the row loop is unrolled by the period (7);
+//   * horizontal neighbours come from an 8-row shared-memory ring of t and 2-row rings of A11 and f = A12 * D_eta t;
+//   * every operand is read from global memory once per point (own column, coalesced) by cp.async into a per-thread
+//     slot of a 4-stage shared-memory ring, three rows ahead of its use (no registers held across the latency);
+//   * the stencil input may be the combination t = x + a v (FD-JVP / line search), formed when a row is consumed;
+//   * divisions by 288 h^2, J, dt and the FD step are multiplications by a correctly rounded reciprocal.
 // One block barrier per row.  Only interior points (4 <= r < ny-4, 4 <= c < nx-4: no closure stencil in reach) are
 // marched; the frame of 4 rows / columns along each edge is done by a few extra CTAs of the same launch with the
-// general per-point formulas (mesh_laplace_general_g), reading t through the same accessor.
+// general per-point formulas (mesh_laplace_general_g), reading t through the same accessor; they run concurrently
+// with the marching CTAs (33 us alone against ~90 us for the interior at 2048^2).
 //
 // Modes: MARCH_LAP        out = Lap t (out2 = t when non-null)
 //        MARCH_PMA2_RESID u = px + pa pv ; F = (u - uval)/dt - (rhs(u, Lap t) + cn)/2 ; out = F ; sum F^2, max|F|, max|u|
 //        MARCH_PMA2_JVP   out = (F - f0)/div
 // Algorithmic bytes per point: LAP 6 fields (t, A11, A22, A12, J in; out) + 1 with v; PMA2 pass 9-11 fields.
+// Measured on B200 at 2048^2 (ncu, profiles/ncu_march_r1.md): 3.2-3.4 TB/s of algorithmic traffic (0.5 of the
+// measured HBM peak; the one-thread-per-point kernels reach 0.24): DRAM traffic equals the algorithmic bytes; the limit
+// is the per-row dependency chain of fp64 operations at 16 resident warps per SM (stall reason "wait"), not a pipe.
 #pragma once
 #include "cuda_common.cuh"
 #include "mesh_kernels.cuh"
@@ -38,7 +45,26 @@ constexpr int kMarchRing = 8;                             // rows of t kept in s
 constexpr int kMarchPad = 4;                              // slack columns so that halo threads index in range
 constexpr int kMarchMinRows = 8;                          // rows per chunk at least (6 warm-up rows per chunk)
 
+constexpr int kMarchAhead = 3;                            // rows of operands in flight ahead of the row being computed
+constexpr int kMarchStages = kMarchAhead + 1;             // cp.async ring depth
+
 enum MarchMode { MARCH_LAP = 0, MARCH_PMA2_RESID = 1, MARCH_PMA2_JVP = 2 };
+// operand fields staged per row by cp.async: stencil input (x, v), A12 and A22 of row r+2, A11 and J of row r, and the
+// pointwise operands of the PMA2 modes (px, pv, uval, cn, f0).  The PMA2 passes never combine their stencil input
+// (HAS_V is false), so pv shares the slot of v: 6 fields per stage for MARCH_LAP, 10 for the PMA2 modes.
+enum MarchField { MF_X = 0, MF_V = 1, MF_PV = 1, MF_A12N, MF_A22, MF_A11, MF_J, MF_PX, MF_UVAL, MF_CN, MF_F0, MF_COUNT };
+__host__ __device__ constexpr int march_fields(int mode) { return mode == MARCH_LAP ? MF_PX : MF_COUNT; }
+constexpr int kMarchW = kMarchThreads + 2 * kMarchPad;
+__host__ __device__ constexpr size_t march_smem_bytes(int mode) {
+  return sizeof(double) * ((size_t)(kMarchRing + 4) * kMarchW + (size_t)kMarchStages * march_fields(mode) * kMarchThreads);
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct MarchArgs {
   MeshGeom gm;
@@ -59,10 +85,13 @@ struct MarchArgs {
 template <int MODE, bool HAS_V>
 __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_kernel(const __grid_constant__ MarchArgs A, double* S,
                                                                        ReduceWs ws) {
-  constexpr int W = kMarchThreads + 2 * kMarchPad;
-  __shared__ double Ts[kMarchRing][W];
-  __shared__ double A11s[2][W];
-  __shared__ double Fs[2][W];
+  constexpr int W = kMarchW;
+  constexpr int NF = march_fields(MODE);
+  extern __shared__ __align__(16) unsigned char march_smem[];
+  double (*Ts)[W] = reinterpret_cast<double (*)[W]>(march_smem);                  // [kMarchRing][W] rows of t
+  double (*A11s)[W] = Ts + kMarchRing;                                             // [2][W]
+  double (*Fs)[W] = A11s + 2;                                                      // [2][W]
+  double* Pf = reinterpret_cast<double*>(Fs + 2);                                  // [stage][field][thread]
   const MeshGeom& g = A.gm;
   const int nx = g.nx, ny = g.ny;
   const int tid = threadIdx.x;
@@ -149,6 +178,7 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
     //   tw[m % 7]           = t(r0 - 3 + m, c)   rows r-3..r+3 of output row r = r0 + u are slots (u + k + 3) % 7
     //   a22w[m % 7], gw[..] = A22, g (r0 - 2 + m, c)   rows r-2..r+2 are slots (u + k + 2) % 7
     double tw[7], a22w[7], gw[7];
+    double a12_0 = 0.0, a12_1 = 0.0, a12_2 = 0.0;
     const double rx = __drcp_rn(288 * g.dksi2), ry = __drcp_rn(288 * g.deta2); // one rounding each, instead of a
                                                                               // division per point and direction
 
@@ -165,45 +195,51 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
       if (m >= 1 && m <= 4) {
         const double* T = Ts[rho & (kMarchRing - 1)] + st;
         const double vk = wx0 * T[-2] + wx1 * T[-1] + wx3 * T[1] + wx4 * T[2];
-        gw[m - 1] = __ldg(A12p + off) * vk;
+        a12_1 = a12_2; a12_2 = __ldg(A12p + off); // ends with A12 of rows r0, r0+1
+        gw[m - 1] = a12_2 * vk;
         a22w[m - 1] = __ldg(A22p + off);
       }
     }
 
-    // software pipeline: the operands of iteration r are loaded during iteration r-1
-    double n_x, n_v = 0.0, n_a12r, n_a12, n_a22, n_a11, n_J;
-    auto prefetch = [&](int r) {
-      const size_t o3 = (size_t)(r + 3) * nx + c, o2 = (size_t)(r + 2) * nx + c, o0 = (size_t)r * nx + c;
-      n_x = __ldg(A.x + o3);
-      if (HAS_V) n_v = __ldg(A.v + o3);
-      n_a12 = __ldg(A12p + o2);
-      n_a22 = __ldg(A22p + o2);
-      n_a12r = __ldg(A12p + o0); // second touch of this element (first: two rows ago): an L1/L2 hit, saves a window
-      n_a11 = __ldg(A11p + o0);
-      n_J = __ldg(Jp + o0);
+    // Operand pipeline: the global operands of row r (own column of every field) are copied into a per-thread slot
+    // of a shared-memory ring by cp.async kMarchAhead rows before they are used -- ~4 us of loads in flight per
+    // thread without holding a register, enough to cover HBM latency under load.  A thread only ever reads the slots
+    // it filled itself, so completion is tracked with cp.async groups and needs no barrier.
+    auto issue = [&](int r) {
+      if (r < r1) {
+        double* pf = Pf + (size_t)(r & (kMarchStages - 1)) * NF * kMarchThreads + tid;
+        const size_t o3 = (size_t)(r + 3) * nx + c, o2 = (size_t)(r + 2) * nx + c, o0 = (size_t)r * nx + c;
+        cp_async8(pf + MF_X * kMarchThreads, A.x + o3);
+        if (HAS_V) cp_async8(pf + MF_V * kMarchThreads, A.v + o3);
+        cp_async8(pf + MF_A12N * kMarchThreads, A12p + o2);
+        cp_async8(pf + MF_A22 * kMarchThreads, A22p + o2);
+        cp_async8(pf + MF_A11 * kMarchThreads, A11p + o0);
+        cp_async8(pf + MF_J * kMarchThreads, Jp + o0);
+        if (MODE != MARCH_LAP) {
+          cp_async8(pf + MF_PX * kMarchThreads, A.px + o0);
+          if (has_pv) cp_async8(pf + MF_PV * kMarchThreads, A.pv + o0);
+          cp_async8(pf + MF_UVAL * kMarchThreads, A.uval + o0);
+          cp_async8(pf + MF_CN * kMarchThreads, A.cn + o0);
+          if (MODE == MARCH_PMA2_JVP) cp_async8(pf + MF_F0 * kMarchThreads, A.f0 + o0);
+        }
+      }
+      cp_async_commit(); // (an empty group past the last row keeps the group count uniform)
     };
-    prefetch(r0);
+#pragma unroll
+    for (int k = 0; k < kMarchAhead; ++k) issue(r0 + k);
     for (int rb = r0; rb < r1; rb += 7) {
 #pragma unroll
       for (int u = 0; u < 7; ++u) {
         const int r = rb + u;
         if (r >= r1) break;
-        // take the prefetched row
-        const double tnew = HAS_V ? combine(n_x, a, n_v) : n_x;
+        issue(r + kMarchAhead);
+        cp_async_wait<kMarchAhead>(); // the group of row r has landed
+        const double* pf = Pf + (size_t)(r & (kMarchStages - 1)) * NF * kMarchThreads + tid;
+        const double tnew = HAS_V ? combine(pf[MF_X * kMarchThreads], a, pf[MF_V * kMarchThreads]) : pf[MF_X * kMarchThreads];
         tw[(u + 6) % 7] = tnew;
-        a22w[(u + 4) % 7] = n_a22;
-        const double a12r2 = n_a12, a12r = n_a12r, a11 = n_a11, Jv = n_J;
-        if (r + 1 < r1) prefetch(r + 1);
-        // pointwise operands of this row: issued here, consumed after the barrier
-        double uu = 0.0, pvv = 0.0, uval = 0.0, cn = 0.0, f0 = 0.0;
-        if (MODE != MARCH_LAP) {
-          const size_t o0 = (size_t)r * nx + c;
-          uu = __ldg(A.px + o0);
-          if (has_pv) pvv = __ldg(A.pv + o0);
-          uval = __ldg(A.uval + o0);
-          cn = __ldg(A.cn + o0);
-          if (MODE == MARCH_PMA2_JVP) f0 = __ldg(A.f0 + o0);
-        }
+        a22w[(u + 4) % 7] = pf[MF_A22 * kMarchThreads];
+        a12_0 = a12_1; a12_1 = a12_2; a12_2 = pf[MF_A12N * kMarchThreads]; // A12 of rows r, r+1, r+2
+        const double a12r2 = a12_2, a12r = a12_0, a11 = pf[MF_A11 * kMarchThreads];
 
         const int slot = r & 1;
         Ts[(r + 3) & (kMarchRing - 1)][st] = tnew;
@@ -236,9 +272,16 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
           double accx = 0.0, accy = 0.0;
           accx += wx0 * FX[-2]; accx += wx1 * FX[-1]; accx += wx3 * FX[1]; accx += wx4 * FX[2];
           accy += wy0 * GW(-2); accy += wy1 * GW(-1); accy += wy3 * GW(1); accy += wy4 * GW(2);
-          const double rJ = __drcp_rn(Jv);
+          const double rJ = __drcp_rn(pf[MF_J * kMarchThreads]);
           const double lap = (xx + accx) * rJ + (yy + accy) * rJ;
-          if (has_pv) uu = combine(uu, pa, pvv);
+          double uu = 0.0, uval = 0.0, cn = 0.0, f0 = 0.0;
+          if (MODE != MARCH_LAP) {
+            uu = pf[MF_PX * kMarchThreads];
+            if (has_pv) uu = combine(uu, pa, pf[MF_PV * kMarchThreads]);
+            uval = pf[MF_UVAL * kMarchThreads];
+            cn = pf[MF_CN * kMarchThreads];
+            if (MODE == MARCH_PMA2_JVP) f0 = pf[MF_F0 * kMarchThreads];
+          }
           emit((size_t)r * nx + c, false, TW(0), lap, uu, uval, cn, f0);
         }
 #undef TW
