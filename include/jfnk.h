@@ -124,6 +124,13 @@ size_t jfnk_workspace_bytes(const jfnk_config* cfg);
 int jfnk_create(const jfnk_config* cfg, void* dworkspace, size_t workspace_bytes, jfnk_ctx** out);
 int jfnk_destroy(jfnk_ctx* ctx);
 int jfnk_set_callback(jfnk_ctx* ctx, jfnk_callback cb, void* user);
+/* Preconditioner of the inner LGMRES in jfnk_newton: scipy.optimize.newton_krylov's inner_M (_nonlin.py:1398-1410, :1516),
+ * which SciPy hands to lgmres as M, i.e. a LEFT preconditioner (lgmres.py:169 v0 = -psolve(r_outer); _gcrotmk.py:113-121
+ * w = lpsolve(matvec(z))).  dout = M din on device vectors of the context's local length; the callee enqueues its work on the
+ * context's stream (or synchronises) and returns 0 on success.  fn = NULL removes it.  The reference never sets inner_M;
+ * this is the SURVEY.md section 8f hook that makes the fixed-domain large-N Swift-Hohenberg / PMA2 cases tractable. */
+typedef int (*jfnk_psolve_fn)(void* user, const double* din, double* dout);
+int jfnk_set_preconditioner(jfnk_ctx* ctx, jfnk_psolve_fn fn, void* user);
 
 /* ---- multi-GPU plumbing (slab decomposition; NCCL send/recv halos + allreduce) ---------------- */
 /* rank 0 fills a 128-byte NCCL unique id; the host layer broadcasts it (torch.distributed). */
@@ -189,6 +196,10 @@ int jfnk_pma2_set_prev(jfnk_ctx* ctx, const double* dUval);
 /* Droplet: parameters (droplet.py:23-53) and per-step precompute U.val, F=pde_rhs, dt (droplet.py:373-381). */
 int jfnk_droplet_setup(jfnk_ctx* ctx, double epsilon, int n_exp, int m_exp, double Bo, double alpha2, double epsilon2);
 int jfnk_droplet_set_prev(jfnk_ctx* ctx, const double* dUval, double dt);
+/* compute_U2 / compute_U (droplet.py:413-429, :544-551): the analytic initial shape
+ * dU = eps + (1 - eps) sum_i H2(G2(|(Q_ksi, Q_eta) - (x_i, y_i)|, R_i), R_i, V_i) on the mesh given by the potential dQ;
+ * info_host = ndrops x (x, y, R, V) (<= 8 droplets), a = steepness of the smoothed contact line (a_ = 100, :24). */
+int jfnk_droplet_shape(jfnk_ctx* ctx, const double* dQ, int ndrops, const double* info_host, double a, double* dU);
 
 /* Moving-mesh relaxation on the device: `loops` passes of { compute_Q_spatial_ders; J; Laplace_operator(U.val);
  * compute_and_smooth_monitor; solve_PMA (2-D DCT-II solve); Q += dt_mesh * Q_t } -- loop_pma of droplet.py:590-599

@@ -10,11 +10,13 @@ The directory name contains hyphens; import it through the root-level alias modu
 """
 from .context import Context, CudaBuffers, HistoryBuffer, NoConvergence
 from .nonlin import newton_krylov
+from .precond import SHFourierPreconditioner
 from .residuals import (DropletResidual, PMA2Residual, SHLinearised, SHResidual, load_droplet_state,
                         save_droplet_state)
 from .slab import SlabComm, seeded_slab_state, slab_rows
 
 __all__ = [
+    "SHFourierPreconditioner",
     "newton_krylov", "NoConvergence", "SHResidual", "SHLinearised", "PMA2Residual", "DropletResidual",
     "Context", "CudaBuffers", "HistoryBuffer", "SlabComm", "slab_rows", "seeded_slab_state",
     "load_droplet_state", "save_droplet_state",

@@ -49,6 +49,7 @@ class KernelStat(C.Structure):
 
 
 CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double)
+PSOLVE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
 
 _P = C.c_void_p  # device pointers travel as plain addresses
 _CTX = C.c_void_p
@@ -62,6 +63,7 @@ SIGNATURES = {
     "jfnk_create": (C.c_int, [C.POINTER(Config), _P, C.c_size_t, C.POINTER(_CTX)]),
     "jfnk_destroy": (C.c_int, [_CTX]),
     "jfnk_set_callback": (C.c_int, [_CTX, CALLBACK, C.c_void_p]),
+    "jfnk_set_preconditioner": (C.c_int, [_CTX, PSOLVE, C.c_void_p]),
     "jfnk_comm_unique_id": (C.c_int, [C.c_void_p]),
     "jfnk_comm_init": (C.c_int, [_CTX, C.c_void_p]),
     "jfnk_comm_peer_memory": (C.c_int, [_CTX]),
@@ -86,6 +88,7 @@ SIGNATURES = {
     "jfnk_pma2_set_prev": (C.c_int, [_CTX, _P]),
     "jfnk_droplet_setup": (C.c_int, [_CTX, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
     "jfnk_droplet_set_prev": (C.c_int, [_CTX, _P, C.c_double]),
+    "jfnk_droplet_shape": (C.c_int, [_CTX, _P, C.c_int, C.POINTER(C.c_double), C.c_double, _P]),
     "jfnk_mesh_relax": (C.c_int, [_CTX, _P, _P, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]),
     "jfnk_launch_count": (C.c_int64, [_CTX]),
     "jfnk_profile_enable": (C.c_int, [_CTX, C.c_int]),

@@ -67,6 +67,15 @@ class CudaBuffers:
             return t.reshape(like.shape)
         return t.cpu().numpy().reshape(np.shape(like))
 
+    def raw_view(self, ptr, n):
+        """a flat fp64 tensor aliasing ``n`` doubles of device memory at ``ptr`` (no copy): what a preconditioner sees"""
+        torch = self.torch
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+        return torch.as_tensor(_Raw(), device=self.device)
+
     def attach_comm(self, comm, ctx):
         from .slab import attach_nccl
 

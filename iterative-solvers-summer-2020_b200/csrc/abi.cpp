@@ -95,6 +95,14 @@ int jfnk_set_callback(jfnk_ctx* ctx, jfnk_callback cb, void* user) {
   return JFNK_OK;
 }
 
+int jfnk_set_preconditioner(jfnk_ctx* ctx, jfnk_psolve_fn fn, void* user) {
+  JF_TRY
+  JF_CHECK_CTX(ctx);
+  ctx->eng->set_preconditioner(fn, user);
+  return JFNK_OK;
+  JF_CATCH
+}
+
 int jfnk_comm_unique_id(void* id128) {
   std::string why;
   int rc = backend_unique_id(id128, why);
@@ -186,6 +194,9 @@ int jfnk_droplet_setup(jfnk_ctx* ctx, double epsilon, int n_exp, int m_exp, doub
   dp.epsilon2 = epsilon2; dp.dt = 0.0;
   return done(ctx, ctx->eng->droplet_setup(dp));
   JF_CATCH
+}
+int jfnk_droplet_shape(jfnk_ctx* ctx, const double* dQ, int ndrops, const double* info_host, double a, double* dU) {
+  JF_TRY JF_CHECK_CTX(ctx); return done(ctx, ctx->eng->droplet_shape(dQ, ndrops, info_host, a, dU)); JF_CATCH
 }
 int jfnk_droplet_set_prev(jfnk_ctx* ctx, const double* dUval, double dt) {
   JF_TRY JF_CHECK_CTX(ctx); return done(ctx, ctx->eng->droplet_set_prev(dUval, dt)); JF_CATCH

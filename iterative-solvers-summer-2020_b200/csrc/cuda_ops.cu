@@ -598,6 +598,11 @@ class CudaOps : public DeviceOps {
     Prof prof(this, K_MESH, nb(7));
     droplet_div_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), A, B, out);
   }
+  void droplet_shape(const MeshParams& mp, const double* Q, const DropList& drops, double a, double eps, double* out) override {
+    MeshGeom gm = geom(mp);
+    Prof prof(this, K_MESH, nb(2));
+    droplet_shape_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, Q, drops, a, eps, out);
+  }
   void droplet_combine(const DropletParams& dp, const double* u, const double* uval, const double* F2,
                        const double* Fprev, double* F, int norm_off) override {
     Prof prof(this, K_MESH, nb(5));

@@ -43,6 +43,12 @@ struct MeshParams {
   double dksi, deta;
   double bl, br, bb, bt; // Dirichlet values of Q_ksi (left,right) and Q_eta (bottom,top)
 };
+// droplets of an initial state: centre (x, y), radius R, volume V (droplet.py:126 `info`)
+constexpr int kMaxDrops = 8;
+struct DropList {
+  int n;
+  double x[kMaxDrops], y[kMaxDrops], R[kMaxDrops], V[kMaxDrops];
+};
 struct Pma2Params { double lambd, beta, epsilon; int m; double dt; };
 struct DropletParams { double epsilon; int n_exp, m_exp; double Bo, alpha2, epsilon2; double dt; };
 
@@ -176,6 +182,11 @@ class DeviceOps {
   // F = (u - uval) - dt (F2 + Fprev)/2 ; norms as sh_residual
   virtual void droplet_combine(const DropletParams& dp, const double* u, const double* uval, const double* F2,
                                const double* Fprev, double* F, int norm_off) = 0;
+
+  // droplet initial shape on the current mesh (compute_U2 / compute_U, droplet.py:413-429,544-551):
+  // out = eps + (1 - eps) sum_i H2(G2(|(Q_ksi, Q_eta) - (x_i, y_i)|, R_i), R_i, V_i)
+  virtual void droplet_shape(const MeshParams& mp, const double* Q, const DropList& drops, double a, double eps,
+                             double* out) = 0;
 
   // ---- moving-mesh relaxation (loop_pma / solve_PMA; PMA2_nk.py:345-403, droplet.py:578-599,729-760) ------
   // out = monitor(u, lap): mode 0 |lap|^2, mode 1 1/(1+u)^6

@@ -246,6 +246,23 @@ int Engine::mesh_relax(double* Q, const double* Uval, double dt, int loops, cons
   return ops_->status();
 }
 
+// compute_U2 (droplet.py:413-423): the analytic droplet shapes on the current mesh; info = ndrops x (x, y, R, V).
+int Engine::droplet_shape(const double* Q, int ndrops, const double* info, double a, double* U) {
+  if (cfg_.problem != JFNK_PROBLEM_DROPLET) return fail(JFNK_INVALID, "jfnk_droplet_shape: droplet problem only");
+  if (!mesh_ready_ || !dp_ready_) return fail(JFNK_INVALID, "jfnk_droplet_shape: call jfnk_mesh_setup and jfnk_droplet_setup first");
+  if (ndrops < 0 || ndrops > kMaxDrops || (ndrops > 0 && !info)) return fail(JFNK_INVALID, "jfnk_droplet_shape: 0..8 droplets");
+  if (!(a > 0)) return fail(JFNK_INVALID, "jfnk_droplet_shape: the interface steepness a must be positive");
+  DropList dl;
+  memset(&dl, 0, sizeof(dl));
+  dl.n = ndrops;
+  for (int i = 0; i < ndrops; ++i) {
+    dl.x[i] = info[4 * i]; dl.y[i] = info[4 * i + 1]; dl.R[i] = info[4 * i + 2]; dl.V[i] = info[4 * i + 3];
+    if (!(dl.R[i] > 0)) return fail(JFNK_INVALID, "jfnk_droplet_shape: radii must be positive");
+  }
+  ops_->droplet_shape(mp_, Q, dl, a, dp_.epsilon, U);
+  return ops_->status();
+}
+
 bool Engine::problem_ready(std::string& why) const {
   switch (cfg_.problem) {
     case JFNK_PROBLEM_SH:
@@ -408,7 +425,15 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
     zs[j] = z; znidx[j] = zi;
     double* w = VS_[j];
     vs[j + 1] = w;
-    apply_operator(z, zi, w, true);
+    if (psolve_ && op_tmp_) {
+      // left preconditioning (_gcrotmk.py:113-121): w = M (A z)
+      apply_operator(z, zi, op_tmp_, true);
+      int st0 = ops_->status();
+      if (st0) return st0;
+      if (psolve_(psolve_user_, op_tmp_, w) != 0) return fail(JFNK_INVALID, "the preconditioner callback reported an error");
+    } else {
+      apply_operator(z, zi, w, true);
+    }
     // classical Gram-Schmidt against vs[0..j]: all dots in one fused reduction, then one fused update.
     // One host round-trip per Arnoldi step: {w.w, ||w||^2 after pass 1, residual estimate, flags}.  The host
     // decides from it whether a second (re-orthogonalisation) pass is needed; only then more work is enqueued.
@@ -532,6 +557,7 @@ int Engine::lgmres(const double* b, double* x, double rtol, int maxiter, int* in
     return fail(JFNK_INVALID, "jfnk_lgmres: call jfnk_linearize first");
   }
   if (maxiter < 1) return fail(JFNK_INVALID, "jfnk_lgmres: maxiter must be >= 1");
+  if (psolve_) return fail(JFNK_INVALID, "jfnk_lgmres: the preconditioner hook applies to jfnk_newton only; remove it first");
   return lgmres_general(b, x, rtol, maxiter, info, res, inner);
 }
 
@@ -603,7 +629,22 @@ int Engine::newton(double* u, const jfnk_newton_opts* o, jfnk_history* hist) {
       // lgmres breaks before the first cycle (lgmres.py:166-167): solution stays 0
       return fail(JFNK_ZERO_STEP, "Jacobian inversion yielded zero vector.");
     }
-    rc = cycle(Fx, f2, ptol, co);
+    if (psolve_) {
+      // lgmres.py:169-178: v0 = M b (sign carried by dx = -sol), inner_res_0 = ||v0||; the trial buffers are free until
+      // the line search: Ft holds v0 for the whole cycle, xt receives A z before M is applied
+      if (psolve_(psolve_user_, Fx, Ft) != 0) return fail(JFNK_INVALID, "the preconditioner callback reported an error");
+      ops_->mdot(0, nullptr, Ft, JS_TMP3);
+      ops_->allreduce_sum(JS_TMP3, 1);
+      double v0n2 = 0.0;
+      ops_->read_scalars(JS_TMP3, 1, &v0n2);
+      if (!isfinite(v0n2)) return fail(JFNK_NONFINITE, "the preconditioner returned non-finite values");
+      if (v0n2 == 0.0) return fail(JFNK_INVALID, "Preconditioner returned a zero vector");
+      op_tmp_ = xt;
+      rc = cycle(Ft, v0n2, ptol, co);
+      op_tmp_ = nullptr;
+    } else {
+      rc = cycle(Fx, f2, ptol, co);
+    }
     if (rc) return rc;
     if (co.sol_n2 == 0.0)
       return fail(JFNK_ZERO_STEP, "Jacobian inversion yielded zero vector. This indicates a bug in the Jacobian approximation.");

@@ -38,6 +38,7 @@ class Engine {
   const Grid& grid() const { return grid_; }
   const std::string& error() const { return err_; }
   void set_callback(jfnk_callback cb, void* user) { cb_ = cb; cb_user_ = user; }
+  void set_preconditioner(jfnk_psolve_fn fn, void* user) { psolve_ = fn; psolve_user_ = user; }
 
   // problem setup
   int sh_setup(double h, double r, double g, double k);
@@ -53,6 +54,7 @@ class Engine {
   int droplet_setup(const DropletParams& dp);
   int droplet_set_prev(const double* uval, double dt);
   int mesh_relax(double* Q, const double* Uval, double dt, int loops, const PmaParams& pp);
+  int droplet_shape(const double* Q, int ndrops, const double* info, double a, double* U);
 
   // operator level
   int residual(const double* u, double* F);
@@ -83,6 +85,9 @@ class Engine {
   std::string err_;
   jfnk_callback cb_ = nullptr;
   void* cb_user_ = nullptr;
+  jfnk_psolve_fn psolve_ = nullptr; // left preconditioner of the inner solve (inner_M); used by newton() only
+  void* psolve_user_ = nullptr;
+  double* op_tmp_ = nullptr;        // where A z is formed before M is applied (a buffer newton() has free)
 
   // workspace vectors
   double* ws_;

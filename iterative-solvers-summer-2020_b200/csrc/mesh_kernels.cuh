@@ -87,6 +87,11 @@ __global__ void __launch_bounds__(256) droplet_div_kernel(MeshGeom gm, MetricCPt
   for_each_point_tiled(gm, [&](int r, int c, size_t e) { out[e] = droplet_div_point(gm, M.m, A, B, r, c); });
 }
 
+__global__ void __launch_bounds__(256) droplet_shape_kernel(MeshGeom gm, const double* Q, DropList dl, double a, double eps,
+                                                            double* out) {
+  for_each_point_tiled(gm, [&](int r, int c, size_t e) { out[e] = droplet_shape_point(gm, Q, r, c, dl, a, eps); });
+}
+
 __global__ void __launch_bounds__(256) droplet_combine_kernel(size_t n, DropletParams dp, const double* u,
                                                               const double* uval, const double* F2, const double* Fprev,
                                                               double* F, double* S, int norm_off, ReduceWs ws) {

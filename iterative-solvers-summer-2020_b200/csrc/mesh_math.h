@@ -323,6 +323,24 @@ JF_HD double droplet_combine_point(const DropletParams& p, double u, double uval
 }
 
 
+// ---- droplet initial shapes (droplet.py:413-429 compute_U2 / G2 / H2 ; :544-551 compute_U / G / H) ------------
+// U = eps + (1 - eps) sum_drops H2(G2(|X - X_drop|, R), R, V) at the PHYSICAL position X = (Q_ksi, Q_eta) of the mesh
+// point (compute_Q_spatial_ders, droplet.py:701-705: Dirichlet values on the edges).
+JF_HD double droplet_G2(double xx, double R, double a) {
+  return R + log((1 + exp(-2 * a * (xx + R))) / (1 + exp(-2 * a * (xx - R)))) / (2 * a);
+}
+JF_HD double droplet_H2(double psi, double R, double V) { return 4 * V * (1 - psi * psi / (R * R)) / (R * R); }
+JF_HD double droplet_shape_point(const MeshGeom& g, const double* Q, int r, int c, const DropList& dl, double a, double eps) {
+  double x = (c == 0) ? g.bl : (c == g.nx - 1 ? g.br : d_ksi(g, Q, r, c));
+  double y = (r == 0) ? g.bb : (r == g.ny - 1 ? g.bt : d_eta(g, Q, r, c));
+  double ret = eps;
+  for (int i = 0; i < dl.n; ++i) {
+    double dx = x - dl.x[i], dy = y - dl.y[i];
+    ret += (1 - eps) * droplet_H2(droplet_G2(sqrt(dx * dx + dy * dy), dl.R[i], a), dl.R[i], dl.V[i]);
+  }
+  return ret;
+}
+
 // ---- moving-mesh relaxation (PMA): monitor function, smoothing filter, spectral solve -------------------
 // compute_and_smooth_monitor (PMA2_nk.py:345-391, droplet.py:729-760), solve_PMA (PMA2_nk.py:393-403,
 // droplet.py:578-588), loop_pma (droplet.py:590-599).

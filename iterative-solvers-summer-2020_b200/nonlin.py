@@ -25,8 +25,12 @@ def newton_krylov(F, xin, iter=None, rdiff=None, method="lgmres", inner_maxiter=
 
     Same parameters as :func:`scipy.optimize.newton_krylov`; the differences are
       * ``F`` is a device residual handle (``SHResidual``, ``PMA2Residual``, ``DropletResidual``),
-      * ``method`` must be ``'lgmres'`` (the only inner solver the reference uses), ``inner_M`` must be None,
-        ``tol_norm`` must be None (max-norm),
+      * ``method`` must be ``'lgmres'`` (the only inner solver the reference uses), ``tol_norm`` must be None (max-norm),
+      * ``inner_M`` (never set by the reference) is a preconditioner acting on DEVICE vectors: a callable or an object
+        with ``matvec`` that maps a flat fp64 device tensor (NumPy array with the CPU test double) to ``M @ v``; as in
+        SciPy it is applied from the left inside LGMRES, and its optional ``update(x, f)`` method is called after every
+        Newton step (KrylovJacobian.update, _nonlin.py:1574-1577).  See :mod:`precond` for a Fourier preconditioner
+        of the Swift-Hohenberg Crank-Nicolson operator,
       * ``inner_maxiter`` is accepted and -- exactly as in SciPy for LGMRES -- has no effect
         (KrylovJacobian overrides ``maxiter=1`` and LGMRES' ``inner_m`` stays 30, _nonlin.py:1503-1506);
         pass ``inner_inner_m=...`` to change the Arnoldi length as SciPy's ``inner_*`` forwarding allows.
@@ -36,8 +40,6 @@ def newton_krylov(F, xin, iter=None, rdiff=None, method="lgmres", inner_maxiter=
                         "there is no CPU path for arbitrary Python callables")
     if method != "lgmres":
         raise NotImplementedError("only method='lgmres' (the reference's inner solver) is implemented")
-    if inner_M is not None:
-        raise NotImplementedError("inner_M (preconditioning) is not used by the reference and not implemented")
     if tol_norm is not None:
         raise NotImplementedError("tol_norm: only the default max-norm is implemented")
     inner_m = 30
@@ -57,12 +59,40 @@ def newton_krylov(F, xin, iter=None, rdiff=None, method="lgmres", inner_maxiter=
     du = ctx.vec(xin, "xin")
     hist = HistoryBuffer()
 
+    n = ctx.n
+    ps_c = None
+    m_update = getattr(inner_M, "update", None) if inner_M is not None else None
+    if inner_M is not None:
+        apply_M = inner_M.matvec if hasattr(inner_M, "matvec") else inner_M
+        if not callable(apply_M):
+            raise TypeError("inner_M must be callable or provide matvec(v)")
+        ps_err = []
+
+        def _ps(_user, pin, pout):
+            try:
+                out = apply_M(ctx.buf.raw_view(pin, n))
+                dst = ctx.buf.raw_view(pout, n)
+                if hasattr(dst, "copy_"):
+                    dst.copy_(out.reshape(-1))
+                else:
+                    dst[:] = out.reshape(-1)
+                return 0
+            except Exception as e:  # no exception may cross the C ABI
+                ps_err.append(e)
+                return 1
+
+        ps_c = _capi.PSOLVE(_ps)
+        if hasattr(inner_M, "setup"):  # KrylovJacobian.setup (_nonlin.py:1594-1598): preconditioner.setup(x, f, func)
+            inner_M.setup(du, F(du), F)
+        ctx.check(ctx.lib.jfnk_set_preconditioner(ctx.handle, ps_c, None))
     cb_c = None
-    if callback is not None:
-        n = ctx.n
+    if callback is not None or m_update is not None:
 
         def _cb(_user, _it, px, pF, _fmax, _fl2):
-            callback(ctx.buf.view_for_callback(px, n, xin), ctx.buf.view_for_callback(pF, n, xin))
+            if m_update is not None:
+                m_update(ctx.buf.raw_view(px, n), ctx.buf.raw_view(pF, n))
+            if callback is not None:
+                callback(ctx.buf.view_for_callback(px, n, xin), ctx.buf.view_for_callback(pF, n, xin))
 
         cb_c = _capi.CALLBACK(_cb)
         ctx.check(ctx.lib.jfnk_set_callback(ctx.handle, cb_c, None))
@@ -71,6 +101,10 @@ def newton_krylov(F, xin, iter=None, rdiff=None, method="lgmres", inner_maxiter=
     finally:
         if cb_c is not None:
             ctx.lib.jfnk_set_callback(ctx.handle, _capi.CALLBACK(), None)
+        if ps_c is not None:
+            ctx.lib.jfnk_set_preconditioner(ctx.handle, _capi.PSOLVE(), None)
+    if inner_M is not None and ps_err:
+        raise ps_err[0]
     h = hist.as_dict()
     F.last_history = h
     if verbose:

@@ -337,6 +337,66 @@ class DropletResidual(_MeshResidual):
         return self
 
 
+    # ---- initial states (droplet.py:132-248, :316-358, :413-429, :544-554) --------------------------------------
+    def uniform_mesh_potential(self):
+        """Q of the undeformed mesh, 0.5 ksi^2 + 0.5 eta^2 (droplet.py:102)."""
+        el, er, eb, et = self.bounds
+        ksi, eta = np.meshgrid(np.linspace(el, er, self.nx), np.linspace(eb, et, self.ny))
+        return np.reshape(0.5 * ksi ** 2 + 0.5 * eta ** 2, self.nx * self.ny)
+
+    def compute_U2(self, Q, info, a=100.0):
+        """``compute_U2(info)`` (droplet.py:413-423) on the mesh with potential ``Q``: the precursor film plus one smoothed
+        parabolic cap per droplet, ``info = [[x, y, R, V], ...]``; evaluated on the device at the physical positions
+        ``(Q_ksi, Q_eta)`` of the mesh points."""
+        ctx = self.context()
+        dQ = ctx.vec(Q, "Q")
+        flat = np.ascontiguousarray(np.asarray(info, dtype=np.float64).reshape(-1, 4))
+        out = ctx.buf.alloc(ctx.n)
+        ctx.check(ctx.lib.jfnk_droplet_shape(ctx.handle, ctx.buf.ptr(dQ), int(flat.shape[0]),
+                                             flat.ctypes.data_as(C.POINTER(C.c_double)), float(a), ctx.buf.ptr(out)))
+        return ctx.buf.to_user(out, Q)
+
+    def compute_U(self, Q, R=1.0, V=1.0, a=100.0):
+        """``compute_U()`` (droplet.py:544-551): one droplet of radius ``R`` and volume ``V`` centred at the origin."""
+        return self.compute_U2(Q, [[0.0, 0.0, R, V]], a)
+
+    def initialise_coalescing_droplets(self, Vsteps, info, dtmesh, loops, Q=None, a=100.0, tofile=None):
+        """``initialise_coalescing_droplets(Vsteps, info, dtmesh, loops, fromfile=False, tofile)`` (droplet.py:132-189):
+        inflate the droplets of ``info`` in ``Vsteps`` volume increments, relaxing the mesh with ``loop_pma(dtmesh, loops)``
+        after each.  Returns ``(U, Q)``; ``tofile`` writes the state in the reference's format (``fromfile`` is
+        :func:`load_droplet_state`)."""
+        Q = self.uniform_mesh_potential() if Q is None else Q
+        Unew = np.full(self.nx * self.ny, self.epsilon)
+        for i in range(1, int(Vsteps) + 1):
+            Uval = Unew
+            Unew = self.compute_U2(Q, [[d[0], d[1], d[2], d[3] * i / Vsteps] for d in info], a)
+            Q = self.relax_mesh(Q, Uval, dtmesh, loops=loops)
+        if tofile:
+            save_droplet_state(tofile, Unew, Q)
+        return Unew, Q
+
+    def initialise_droplet(self, Vsteps, dtmesh, loops, R=1.0, Vf=1.0, Q=None, a=100.0, tofile=None):
+        """``initialise_droplet`` (droplet.py:192-248): the single-droplet version (``compute_U`` with V = Vf i/Vsteps)."""
+        return self.initialise_coalescing_droplets(Vsteps, [[0.0, 0.0, R, Vf]], dtmesh, loops, Q=Q, a=a, tofile=tofile)
+
+    def evolve_R_explicit(self, U, Q, pmaloops, Rfinal, tol, R=1.0, V=1.0, dtR=5e-2, dtmesh=1e-7, a=100.0, max_iters=None):
+        """``evolve_R_explicit`` (droplet.py:316-358): R' = (8V/R^3 - 1)/(3 log(1/eps)) (Rdot, :553-554) by explicit Euler with
+        ``dt = dtR R^2``, ``U = compute_U()`` and a mesh relaxation per step.  As in the script the first relaxation pass
+        still sees the previous ``U`` (its derivatives are refreshed before ``U.val`` is replaced).  Returns (U, Q, R, t)."""
+        time, it = 0.0, 0
+        while abs(Rfinal - R) > tol and (max_iters is None or it < max_iters):
+            dt = dtR * (R ** 2)
+            R += dt * (8 * V / R ** 3 - 1) / (3 * np.log(1 / self.epsilon))
+            Unew = self.compute_U(Q, R, V, a)
+            Q = self.relax_mesh(Q, U, dtmesh, loops=1)
+            if pmaloops > 1:
+                Q = self.relax_mesh(Q, Unew, dtmesh, loops=pmaloops - 1)
+            U = Unew
+            it += 1
+            time += dt
+        return U, Q, R, time
+
+
 def load_droplet_state(path):
     """Read an ``initdrop_*.txt`` state: one ``U.val[i] Q.val[i]`` pair per line (written by droplet.py:556-562).
     The reference's own reader (droplet.py:564-576) hard-codes a Windows path separator."""

@@ -311,6 +311,47 @@ class DropletOracle:
             self._u_ders()
             self.Q = self.Q + dt * o.solve_pma(self.monitor(), self.met["J"], self.alpha, self.gamma)
 
+    # ---- initial states (droplet.py:132-248, :413-429, :544-554) ---------------------------------------------
+    def compute_U2(self, info, a=100):
+        """:413-423 with G2 (:425-426) and H2 (:428-429) on the current mesh (self.met)"""
+        e = self.epsilon
+        ret = np.full(self.ops.NN, e, dtype=float)
+        for x, y, R, V in info:
+            xx = np.sqrt((self.met["dksi"] - x) ** 2 + (self.met["deta"] - y) ** 2)
+            psi = R + np.log((1 + np.exp(-2 * a * (xx + R))) / (1 + np.exp(-2 * a * (xx - R)))) / (2 * a)
+            ret += (1 - e) * (4 * V * (1 - psi * psi / (R * R)) / (R * R))
+        return ret
+
+    def initialise_coalescing_droplets(self, Vsteps, info, dtmesh, loops, a=100):
+        """:132-189 without the file / plot branches: inflate the droplets in Vsteps volume increments, relaxing the
+        mesh (loop_pma) after each.  Starts from self.Q and U = epsilon (main(), :102-105).  Returns U."""
+        Unew = np.full(self.ops.NN, self.epsilon, dtype=float)
+        for i in range(1, Vsteps + 1):
+            self.Uval = Unew.copy()
+            self.met = self.ops.q_ders(self.Q)
+            self._u_ders()
+            arg = [[d[0], d[1], d[2], d[3] * i / Vsteps] for d in info]
+            Unew = self.compute_U2(arg, a)
+            self.loop_pma(dtmesh, loops)
+        return Unew
+
+    def evolve_R_explicit(self, U, pmaloops, Rfinal, tol, R=1.0, V=1.0, dtR=5e-2, dtmesh=1e-7, a=100, max_iters=None):
+        """:316-358: explicit evolution of the droplet radius R' = Rdot() (:553-554) with U = compute_U() (:544-551);
+        loop_pma's first pass still sees the Laplacian of the previous U.val (the script refreshes U.val after
+        compute_u_spatial_ders).  Returns (U, R, time)."""
+        self.Uval = np.array(U, dtype=float, copy=True)
+        time, it = 0.0, 0
+        while abs(Rfinal - R) > tol and (max_iters is None or it < max_iters):
+            self.met = self.ops.q_ders(self.Q)
+            self._u_ders()
+            dt = dtR * (R ** 2)
+            R += dt * (8 * V / R ** 3 - 1) / (3 * np.log(1 / self.epsilon))
+            self.Uval = self.compute_U2([[0.0, 0.0, R, V]], a)
+            self.loop_pma(dtmesh, pmaloops)
+            it += 1
+            time += dt
+        return self.Uval, R, time
+
     def step(self, U, dt_n, dtmesh=3e-9, pmaloops=400, history=None, **kw):
         """one pass of evolve_with_PDE's loop body (:371-384); returns U.new"""
         self.set_mesh(self.Q)

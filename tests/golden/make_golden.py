@@ -10,6 +10,8 @@ np.loadtxt because the reference's read_from_file hard-codes a Windows path sepa
 Outputs (small, committed):
     pma2_n51.npz      operators, Laplace_operator, CN term, residual and 3 time steps of PMA2_nk.py (N_ = 51)
     droplet_91x61.npz the same for droplet.py from initdrop_coal_1_91-61_100_0.01_0.01_0.1_0.15.txt
+    droplet_init_91x61.npz  droplet.py's initialisers: initialise_coalescing_droplets (4 volume steps), initialise_droplet
+                      (3 steps) followed by evolve_R_explicit (until R = 1.07), each with loop_pma relaxations
 """
 import os
 import sys
@@ -117,6 +119,41 @@ def make_droplet():
     print("droplet_91x61.npz", {k: v.shape for k, v in out.items() if k.startswith("op_")})
 
 
+def make_droplet_init():
+    import contextlib
+    import io
+
+    D = _import_reference("droplet")
+    NN = D.NN_
+    D.make_Ibdy()
+    D.make_M()
+    out = {}
+    quiet = io.StringIO()
+    # initialise_coalescing_droplets(Vsteps, info, dtmesh, loops, fromfile, tofile) from main()'s start state (:102-105)
+    D.Q.val = np.reshape(0.5 * D.ksiksi ** 2 + 0.5 * D.etaeta ** 2, NN)
+    D.U.new = np.full(NN, D.epsilon_)
+    info = [[0, 0, 1, 1], [3, 0, 1, 1]]
+    with contextlib.redirect_stdout(quiet):
+        D.initialise_coalescing_droplets(4, info, 5e-9, 20, False, False)
+    out.update(coal_info=np.array(info, dtype=float), coal_U=D.U.val.copy(), coal_Q=D.Q.val.copy())
+    # initialise_droplet(Vsteps, dtmesh, loops, fromfile, tofile) then evolve_R_explicit(pmaloops, Rfinal, tol)
+    D.Q.val = np.reshape(0.5 * D.ksiksi ** 2 + 0.5 * D.etaeta ** 2, NN)
+    D.U.new = np.full(NN, D.epsilon_)
+    D.V_, D.R_ = 0, 1
+    with contextlib.redirect_stdout(quiet):
+        D.initialise_droplet(3, 5e-9, 20, False, False)
+    out.update(rect_U=D.U.val.copy(), rect_Q=D.Q.val.copy())
+    D.U.new = D.U.val.copy()
+    with contextlib.redirect_stdout(quiet):
+        D.evolve_R_explicit(5, 1.07, 1e-2)
+    out.update(evolveR_U=D.U.val.copy(), evolveR_Q=D.Q.val.copy(), evolveR_R=np.array(float(D.R_)),
+               evolveR_args=np.array([5, 1.07, 1e-2, D.dtR_, D.dtmesh_]))
+    D.R_ = 1
+    np.savez_compressed(os.path.join(HERE, "droplet_init_91x61.npz"), **out)
+    print("droplet_init_91x61.npz", {k: np.shape(v) for k, v in out.items()}, "R after evolve_R_explicit:", float(out["evolveR_R"]))
+
+
 if __name__ == "__main__":
     make_pma2()
     make_droplet()
+    make_droplet_init()

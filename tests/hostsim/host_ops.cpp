@@ -296,6 +296,12 @@ class HostOps : public DeviceOps {
     for (size_t e = 0; e < g_.n(); ++e) F[e] = pma2_combine_point(pp, u[e], uval[e], rhs[e], cn[e]);
     norms(F, u, norm_off);
   }
+  void droplet_shape(const MeshParams& mp, const double* Q, const DropList& drops, double a, double eps, double* out) override {
+    launches_++;
+    MeshGeom gm = geom(mp);
+    for (int r = 0; r < g_.ny; ++r)
+      for (int c = 0; c < g_.nx; ++c) out[(size_t)r * g_.nx + c] = droplet_shape_point(gm, Q, r, c, drops, a, eps);
+  }
   void droplet_pressure(const DropletParams& dp, const double* h, const double* lap, double* p) override {
     launches_++;
     for (size_t e = 0; e < g_.n(); ++e) p[e] = droplet_pressure_point(dp, h[e], lap[e]);

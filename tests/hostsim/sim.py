@@ -64,6 +64,9 @@ class SimBuffers:
         arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(int(n),))
         return np.array(arr, copy=True).reshape(np.shape(like))
 
+    def raw_view(self, ptr, n):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(int(n),))
+
     def synchronize(self):
         pass
 

@@ -250,3 +250,25 @@ def test_droplet_marching_laplace_rectangular_grid(cuda_buffers):
     assert relmax(F(g["op_u"]), g["op_residual"]) < 1e-10
     Q400 = F.relax_mesh(g["state_Q"], g["state_U"], 3e-9, loops=400)
     assert rel(Q400 - g["state_Q"], g["run_Q0"] - g["state_Q"]) < 1e-10
+
+
+def test_droplet_initialisers_vs_reference_golden(buffers):
+    """SURVEY.md section 8f rank 3 on the engine: compute_U2 on the device + mesh relaxation, driven by the host loop of
+    droplet.py:132-248 / :316-358, against the outputs of the reference's own functions.  Tolerances: U 1e-11 relative
+    to max (exp / log of the smoothed contact line are library functions on both sides), mesh increment 1e-9."""
+    g = np.load(os.path.join(GOLD, "droplet_init_91x61.npz"))
+    F = jf.DropletResidual(buffers=buffers)
+    Q0 = F.uniform_mesh_potential()
+    U, Q = F.initialise_coalescing_droplets(4, g["coal_info"].tolist(), 5e-9, 20)
+    assert relmax(U, g["coal_U"]) < 1e-11
+    assert rel(Q - Q0, g["coal_Q"] - Q0) < 1e-9
+    U, Q = F.initialise_droplet(3, 5e-9, 20)
+    assert relmax(U, g["rect_U"]) < 1e-11
+    assert rel(Q - Q0, g["rect_Q"] - Q0) < 1e-9
+    pmaloops, Rfinal, tol, dtR, dtmesh = g["evolveR_args"]
+    U, Q, R, _ = F.evolve_R_explicit(U, Q, int(pmaloops), Rfinal, tol, dtR=dtR, dtmesh=dtmesh)
+    assert abs(R - float(g["evolveR_R"])) < 1e-14
+    assert relmax(U, g["evolveR_U"]) < 1e-11
+    assert rel(Q - Q0, g["evolveR_Q"] - Q0) < 1e-9
+    with pytest.raises(ValueError):
+        F.compute_U2(Q0, [[0.0, 0.0, -1.0, 1.0]])  # non-positive radius

@@ -80,3 +80,23 @@ def test_droplet_oracle_matches_reference_golden():
         assert np.array_equal(U, g[f"run_U{s}"]), s
         assert np.array_equal(o2.Q, g[f"run_Q{s}"]), s
         assert np.allclose([h[0] for h in hist[0]["iters"]], g[f"run_hist{s}"], rtol=0, atol=0)
+
+
+def test_droplet_initialisers_oracle_matches_reference_golden():
+    """compute_U2 / initialise_coalescing_droplets / initialise_droplet /
+    evolve_R_explicit of droplet.py, restated in oracle/mesh.py, bit for bit against the reference's own functions."""
+    g = np.load(os.path.join(GOLD, "droplet_init_91x61.npz"))
+    o = DropletOracle()
+    ksi, eta = o.ops.ksiksi.reshape(-1), o.ops.etaeta.reshape(-1)
+    Q0 = 0.5 * ksi ** 2 + 0.5 * eta ** 2
+    o.Q = Q0.copy()
+    U = o.initialise_coalescing_droplets(4, g["coal_info"].tolist(), 5e-9, 20)
+    assert np.array_equal(U, g["coal_U"]) and np.array_equal(o.Q, g["coal_Q"])
+    o = DropletOracle()
+    o.Q = Q0.copy()
+    U = o.initialise_coalescing_droplets(3, [[0.0, 0.0, 1.0, 1.0]], 5e-9, 20)
+    assert np.array_equal(U, g["rect_U"]) and np.array_equal(o.Q, g["rect_Q"])
+    pmaloops, Rfinal, tol, dtR, dtmesh = g["evolveR_args"]
+    U, R, _ = o.evolve_R_explicit(U, int(pmaloops), Rfinal, tol, R=1.0, V=1.0, dtR=dtR, dtmesh=dtmesh)
+    assert R == float(g["evolveR_R"])
+    assert np.array_equal(U, g["evolveR_U"]) and np.array_equal(o.Q, g["evolveR_Q"])
