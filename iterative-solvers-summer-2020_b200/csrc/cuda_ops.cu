@@ -15,6 +15,7 @@
 #include "mesh_kernels.cuh"
 #include "mesh_march.cuh"
 #include "pma_kernels.cuh"
+#include "pma_relax.cuh"
 #include "nccl_dl.h"
 #include "p2p_kernels.cuh"
 #include "sh_kernels.cuh"
@@ -632,15 +633,65 @@ class CudaOps : public DeviceOps {
     Prof prof(this, K_MESH, 8.0 * ((double)M * K + (double)K * N + (double)M * N));
     small_gemm_kernel<<<grid, 256, 0, stream_>>>(M, N, K, A, ta, B, tb, C);
   }
-  void pma_dct2(const double* in, double* tmp, double* out, int inverse) override {
+  bool ensure_dct() {
     const int nx = g_.nx, ny = g_.ny;
     if (!dctx_) {
-      if (!ck(cudaMalloc(&dctx_, sizeof(double) * (size_t)nx * nx), "cudaMalloc(dct)")) return;
-      if (!ck(cudaMalloc(&dcty_, sizeof(double) * (size_t)ny * ny), "cudaMalloc(dct)")) return;
+      if (!ck(cudaMalloc(&dctx_, sizeof(double) * (size_t)nx * nx), "cudaMalloc(dct)")) return false;
+      if (!ck(cudaMalloc(&dcty_, sizeof(double) * (size_t)ny * ny), "cudaMalloc(dct)")) return false;
       dct_matrix_kernel<<<stream_grid((size_t)nx * nx, 256), 256, 0, stream_>>>(nx, dctx_);
       dct_matrix_kernel<<<stream_grid((size_t)ny * ny, 256), 256, 0, stream_>>>(ny, dcty_);
       launches_ += 2;
     }
+    return true;
+  }
+  // persistent single-cluster kernel for the reference-sized grids (pma_relax.cuh); JFNK_RELAX_FUSED=0 disables
+  bool mesh_relax_fused(const MeshParams& mp, const PmaParams& pp, double* Q, const double* Uval, double dt, int loops,
+                        int deriv_bc, double* const* M, double* a, double* b, double* t, double* spec) override {
+    static const bool off = getenv("JFNK_RELAX_FUSED") && atoi(getenv("JFNK_RELAX_FUSED")) == 0;
+    const size_t smem = sizeof(double) * ((size_t)g_.nx * g_.nx + (size_t)g_.ny * g_.ny + g_.n());
+    if (off || capturing_ || smem > (size_t)200 * 1024 || loops < 1) return false;
+    if (!ensure_dct()) return false;
+    RelaxArgs A;
+    memset(&A, 0, sizeof(A));
+    A.gm = geom(mp);
+    A.pp = pp; A.dt = dt; A.cell = mp.dksi * mp.deta; A.loops = loops; A.deriv_bc = deriv_bc;
+    A.Q = Q; A.Uval = Uval;
+    for (int i = 0; i < 7; ++i) A.M.m[i] = M[i];
+    A.a = a; A.b = b; A.t = t; A.spec = spec;
+    A.dctx = dctx_; A.dcty = dcty_;
+    A.partials = ws_.partials;
+    // one cluster: 16 CTAs (non-portable size, opt-in) when the device can schedule it, else 8
+    if (relax_cluster_ == 0) {
+      relax_cluster_ = -1;
+      if (cudaFuncSetAttribute(pma_relax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess) {
+        cudaFuncSetAttribute(pma_relax_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        for (int cs : {16, 8}) {
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kRelaxThreads); cfg.dynamicSmemBytes = smem;
+          cudaLaunchAttribute at;
+          at.id = cudaLaunchAttributeClusterDimension;
+          at.val.clusterDim.x = cs; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+          cfg.attrs = &at; cfg.numAttrs = 1;
+          int nclusters = 0;
+          if (cudaOccupancyMaxActiveClusters(&nclusters, pma_relax_kernel, &cfg) == cudaSuccess && nclusters >= 1) { relax_cluster_ = cs; break; }
+        }
+      }
+      cudaGetLastError();
+    }
+    if (relax_cluster_ < 0) return false;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(relax_cluster_); cfg.blockDim = dim3(kRelaxThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream_;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = relax_cluster_; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    // 12 stages per pass, each a read and a write of a few fields
+    Prof prof(this, K_MESH, nb(30.0) * loops);
+    return ck(cudaLaunchKernelEx(&cfg, pma_relax_kernel, A), "cudaLaunchKernelEx(pma_relax)");
+  }
+  void pma_dct2(const double* in, double* tmp, double* out, int inverse) override {
+    const int nx = g_.nx, ny = g_.ny;
+    if (!ensure_dct()) return;
     if (!inverse) {
       gemm(ny, nx, ny, dcty_, 0, in, 0, tmp);  // Cy . X
       gemm(ny, nx, nx, tmp, 0, dctx_, 1, out); // . Cx^T
@@ -796,6 +847,7 @@ class CudaOps : public DeviceOps {
   bool capturing_ = false;
   int64_t capture_launch0_ = 0, graph_replays_ = 0;
   cudaGraphExec_t graph_exec_ = nullptr;
+  int relax_cluster_ = 0; // 0 untried, -1 unavailable, else the cluster size of pma_relax_kernel
   cudaStream_t cap_stream_ = nullptr, user_stream_ = nullptr;
   bool p2p_ = false;
   void* p2p_block_ = nullptr;

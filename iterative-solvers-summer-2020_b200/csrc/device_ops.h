@@ -60,6 +60,8 @@ struct KernelStat {
   double bytes; // summed ALGORITHMIC bytes of the launches (per-kernel table)
 };
 
+struct PmaParams; // mesh_math.h
+
 class DeviceOps {
  public:
   virtual ~DeviceOps() {}
@@ -189,6 +191,14 @@ class DeviceOps {
                              double* out) = 0;
 
   // ---- moving-mesh relaxation (loop_pma / solve_PMA; PMA2_nk.py:345-403, droplet.py:578-599,729-760) ------
+  // The whole relaxation loop (`loops` passes of: metrics of Q, monitor of Uval, smoothing, regularisation, DCT solve,
+  // Q += dt Q_t) in one launch, when the backend has such a kernel for this grid; false = not done, use the stages below.
+  // M: the 7 metric fields (left holding the values of the last pass's Q); a, b, t, spec: scratch fields.
+  virtual bool mesh_relax_fused(const MeshParams& /*mp*/, const PmaParams& /*pp*/, double* /*Q*/, const double* /*Uval*/,
+                                double /*dt*/, int /*loops*/, int /*deriv_bc*/, double* const* /*M*/, double* /*a*/,
+                                double* /*b*/, double* /*t*/, double* /*spec*/) {
+    return false;
+  }
   // out = monitor(u, lap): mode 0 |lap|^2, mode 1 1/(1+u)^6
   virtual void pma_monitor(int mode, const double* u, const double* lap, double* out) = 0;
   // one pass of the 9-point (edges 6-point, corners 4-point) smoothing filter

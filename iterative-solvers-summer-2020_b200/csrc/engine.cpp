@@ -214,6 +214,12 @@ int Engine::mesh_relax(double* Q, const double* Uval, double dt, int loops, cons
   const int deriv_bc = (cfg_.problem == JFNK_PROBLEM_DROPLET) ? 1 : 0;
   const double cell = mp_.dksi * mp_.deta;
   double *lap = scratch_[0], *a = scratch_[1], *b = scratch_[2], *t = scratch_[3], *spec = scratch_[4];
+  // small grids: the whole loop as one persistent kernel (stages separated by grid barriers, no launches at all)
+  if (ops_->mesh_relax_fused(mp_, pp, Q, Uval, dt, loops, deriv_bc, MF_, a, b, t, spec)) {
+    metrics_ready_ = false;
+    prev_ready_ = false;
+    return ops_->status();
+  }
   auto one_pass = [&]() {
     ops_->mesh_metrics(mp_, Q, MF_);
     if (pp.monitor_mode == 0) ops_->mesh_laplace(mp_, MF_, Uval, lap, nullptr, 1, deriv_bc);

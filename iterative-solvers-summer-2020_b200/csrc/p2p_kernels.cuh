@@ -17,7 +17,7 @@ namespace jfnk {
 constexpr int kP2PMaxRanks = 8;
 constexpr int kP2PMaxScalars = 64;
 constexpr int kP2PHaloSlots = 3; // linearisation point, operand, generic (as CudaOps::halo_ptrs)
-constexpr unsigned long long kP2PTimeoutNs = 20ull * 1000000000ull;
+constexpr unsigned long long kP2PTimeoutNs = 120ull * 1000000000ull; // ranks may start tens of seconds apart
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
