@@ -16,6 +16,11 @@ third-party dependency, SciPy 1.18.1 (``scipy.optimize.newton_krylov`` ->
 The sparse matrices are built with the *same scipy.sparse constructors in the same
 order* as the reference so that CSR storage order -- and therefore the floating-point
 summation order of ``L @ u`` -- is the reference's.
+
+Pinned: tests/golden/sh_n64.npz holds the first three time steps of sh_scipy_nk.py and sh_linearised.py EXECUTED
+UNMODIFIED in the build container (tests/golden/make_golden.py: legacy RNG seeded, the solver call wrapped to record
+and stop); tests/test_oracle.py shows this restatement reproduces their fields and per-iteration Newton norms bit
+for bit.
 """
 from __future__ import annotations
 

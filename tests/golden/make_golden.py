@@ -10,6 +10,10 @@ np.loadtxt because the reference's read_from_file hard-codes a Windows path sepa
 Outputs (small, committed):
     pma2_n51.npz      operators, Laplace_operator, CN term, residual and 3 time steps of PMA2_nk.py (N_ = 51)
     droplet_91x61.npz the same for droplet.py from initdrop_coal_1_91-61_100_0.01_0.01_0.1_0.15.txt
+    sh_n64.npz        the first 3 time steps of sh_scipy_nk.py EXECUTED UNMODIFIED (it has no import guard and would run
+                      2500 steps: its newton_krylov is wrapped to record the result and stop after 3 calls; np.random is
+                      seeded so that its `np.random.randn(N**2)` initial state is reproducible) and of sh_linearised.main()
+                      (spsolve wrapped the same way)
     droplet_init_91x61.npz  droplet.py's initialisers: initialise_coalescing_droplets (4 volume steps), initialise_droplet
                       (3 steps) followed by evolve_R_explicit (until R = 1.07), each with loop_pma relaxations
 """
@@ -153,7 +157,78 @@ def make_droplet_init():
     print("droplet_init_91x61.npz", {k: np.shape(v) for k, v in out.items()}, "R after evolve_R_explicit:", float(out["evolveR_R"]))
 
 
+class _Stop(Exception):
+    pass
+
+
+def make_sh():
+    import contextlib
+    import io
+    import runpy
+
+    import scipy.optimize
+    import scipy.sparse.linalg
+
+    _import_reference("math")  # installs the matplotlib mocks and the reference path
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]  # `import matplotlib.pyplot as plt` binds the attribute
+    sys.modules["matplotlib.pyplot"].subplots.return_value = (MagicMock(), MagicMock())  # fig, ax = plt.subplots(...)
+    out = {}
+    # --- sh_scipy_nk.py: module-level time loop, U = newton_krylov(residual, Uo, verbose=1) (:53-61) ----------------
+    real_nk = scipy.optimize.newton_krylov
+    rec = {"U": [], "hist": []}
+
+    def nk(F, x0, **kw):
+        if not rec["U"]:
+            rec["U0"] = np.array(x0, copy=True)
+        hist = []
+        U = real_nk(F, x0, callback=lambda x, f: hist.append(np.abs(f).max()), **kw)
+        rec["U"].append(np.array(U, copy=True))
+        rec["hist"].append(np.array(hist))
+        if len(rec["U"]) == 3:
+            raise _Stop()
+        return U
+
+    scipy.optimize.newton_krylov = nk
+    np.random.seed(1234)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            runpy.run_path(os.path.join(REF, "sh_scipy_nk.py"))
+    except _Stop:
+        pass
+    finally:
+        scipy.optimize.newton_krylov = real_nk
+    np.random.seed(1234)
+    assert np.array_equal(rec["U0"], np.random.randn(64 ** 2))
+    out.update(nk_U0=rec["U0"], nk_U1=rec["U"][0], nk_U2=rec["U"][1], nk_U3=rec["U"][2],
+               nk_hist1=rec["hist"][0], nk_hist2=rec["hist"][1], nk_hist3=rec["hist"][2])
+    # --- sh_linearised.main(): U = spsolve(I + D - L k/2, (I + L k/2) Uo) (:51-57) ------------------------------------
+    real_sp = scipy.sparse.linalg.spsolve
+    lin = []
+
+    def sp(A, b, *a, **kw):
+        U = real_sp(A, b, *a, **kw)
+        lin.append(np.array(U, copy=True))
+        if len(lin) == 3:
+            raise _Stop()
+        return U
+
+    scipy.sparse.linalg.spsolve = sp
+    np.random.seed(4321)
+    try:
+        SL = _import_reference("sh_linearised")
+        SL.main()
+    except _Stop:
+        pass
+    finally:
+        scipy.sparse.linalg.spsolve = real_sp
+    np.random.seed(4321)
+    out.update(lin_U0=np.random.randn(64 ** 2), lin_U1=lin[0], lin_U2=lin[1], lin_U3=lin[2])
+    np.savez_compressed(os.path.join(HERE, "sh_n64.npz"), **out)
+    print("sh_n64.npz", {k: np.shape(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
+    make_sh()
     make_pma2()
     make_droplet()
     make_droplet_init()

@@ -100,3 +100,24 @@ def test_droplet_initialisers_oracle_matches_reference_golden():
     U, R, _ = o.evolve_R_explicit(U, int(pmaloops), Rfinal, tol, R=1.0, V=1.0, dtR=dtR, dtmesh=dtmesh)
     assert R == float(g["evolveR_R"])
     assert np.array_equal(U, g["evolveR_U"]) and np.array_equal(o.Q, g["evolveR_Q"])
+
+
+def test_sh_oracle_matches_reference_script_golden():
+    """tests/golden/sh_n64.npz holds the first three time steps of sh_scipy_nk.py executed UNMODIFIED (legacy RNG
+    seeded, its newton_krylov wrapped to record and stop) and of sh_linearised.main(): the oracle's restatement
+    reproduces fields and per-iteration Newton norms bit for bit."""
+    from oracle.sh import SHLinearisedOracle
+
+    g = np.load(os.path.join(GOLD, "sh_n64.npz"))
+    o = SHOracle(N=64)
+    U, hist = g["nk_U0"], []
+    for s in (1, 2, 3):
+        U = o.step(U, history=hist)
+        assert np.array_equal(U, g[f"nk_U{s}"]), s
+        assert np.array_equal(np.array([it[0] for it in hist[-1]["iters"]]), g[f"nk_hist{s}"]), s
+    ol = SHLinearisedOracle(N=64)
+    U = g["lin_U0"]
+    Uo = U.copy()
+    for s in (1, 2, 3):
+        U, Uo = ol.step(U, Uo)
+        assert np.array_equal(U, g[f"lin_U{s}"]), s

@@ -339,3 +339,27 @@ def test_preconditioned_newton_krylov_matches_scipy_inner_M(buffers):
     F.set_prev(U0)
     with pytest.raises(ZeroDivisionError):
         jf.newton_krylov(F, U0, inner_M=bad)
+
+
+def test_engine_vs_reference_script_golden(buffers):
+    """The engine against the outputs of the reference scripts themselves (tests/golden/sh_n64.npz: sh_scipy_nk.py and
+    sh_linearised.py executed unmodified for three time steps from a seeded np.random.randn state): fields to 1e-8
+    relative L2, equal Newton iteration counts, first-iteration norm to 5e-2 (FD-JVP noise, see the module docstring)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sh_n64.npz"))
+    F = jf.SHResidual(N=64, buffers=buffers)
+    U = g["nk_U0"]
+    for s in (1, 2, 3):
+        F.set_prev(U)
+        U = jf.newton_krylov(F, U)
+        assert rel(U, g[f"nk_U{s}"]) < 1e-8, s
+        h = F.last_history
+        assert h["nit"] == len(g[f"nk_hist{s}"]), s
+        assert abs(h["f_max"][0] - g[f"nk_hist{s}"][0]) <= 5e-2 * g[f"nk_hist{s}"][0], s
+    FL = jf.SHLinearised(N=64, buffers=buffers)
+    U = g["lin_U0"]
+    Uo = U.copy()
+    for s in (1, 2, 3):
+        U, Uo = FL.steps(U, Uo, nsteps=1)
+        assert rel(U, g[f"lin_U{s}"]) < 1e-10, s
