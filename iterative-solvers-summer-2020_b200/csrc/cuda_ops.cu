@@ -331,29 +331,10 @@ class CudaOps : public DeviceOps {
     }
     if (p2p_) {
       if (exchange) {
-        const unsigned long long e = ++halo_epoch_[slot];
-        const int par = (int)(e & 1ull);
-        const int prev = (g_.rank + g_.nranks - 1) % g_.nranks, next = (g_.rank + 1) % g_.nranks;
-        P2PHaloArgs A;
-        A.src_first = v;
-        A.src_last = v + (size_t)(g_.nrows - 2) * g_.nx;
-        A.dst_prev_bot = p2p_halo(prev, slot, par, 1);
-        A.dst_next_top = p2p_halo(next, slot, par, 0);
-        A.flag_prev_bot = p2p_hflag(prev, slot, 1);
-        A.flag_next_top = p2p_hflag(next, slot, 0);
-        A.my_flag_top = p2p_hflag(g_.rank, slot, 0);
-        A.my_flag_bot = p2p_hflag(g_.rank, slot, 1);
-        A.epoch = e;
-        A.count = 2 * (size_t)g_.nx;
-        A.ticket = ws_.ticket;
-        A.err = p2p_err();
-        const int blocks = (int)std::max<size_t>(1, std::min<size_t>(32, (A.count + 1023) / 1024));
-        Prof prof(this, K_HALO, 4.0 * 8.0 * (double)A.count); // two messages out, two in
-        p2p_halo_kernel<<<blocks, 256, 0, stream_>>>(A);
+        P2PHaloArgs A = p2p_next_exchange(v, slot);
+        p2p_run_exchange(A);
       }
-      const int par = (int)(halo_epoch_[slot] & 1ull);
-      top = p2p_halo(g_.rank, slot, par, 0);
-      bot = p2p_halo(g_.rank, slot, par, 1);
+      p2p_my_halos(slot, top, bot);
       return;
     }
     double* t = halo_[2 * slot];
@@ -371,6 +352,53 @@ class CudaOps : public DeviceOps {
       nck(nccl_->GroupEnd(), "ncclGroupEnd");
     }
     top = t; bot = b;
+  }
+
+  // peer-memory exchange of the 2-row halos of v for `slot`: allocate the next epoch and describe it ...
+  P2PHaloArgs p2p_next_exchange(const double* v, int slot) {
+    const unsigned long long e = ++halo_epoch_[slot];
+    const int par = (int)(e & 1ull);
+    const int prev = (g_.rank + g_.nranks - 1) % g_.nranks, next = (g_.rank + 1) % g_.nranks;
+    P2PHaloArgs A;
+    A.src_first = v;
+    A.src_last = v + (size_t)(g_.nrows - 2) * g_.nx;
+    A.dst_prev_bot = p2p_halo(prev, slot, par, 1);
+    A.dst_next_top = p2p_halo(next, slot, par, 0);
+    A.flag_prev_bot = p2p_hflag(prev, slot, 1);
+    A.flag_next_top = p2p_hflag(next, slot, 0);
+    A.my_flag_top = p2p_hflag(g_.rank, slot, 0);
+    A.my_flag_bot = p2p_hflag(g_.rank, slot, 1);
+    A.epoch = e;
+    A.count = 2 * (size_t)g_.nx;
+    A.ticket = p2p_ticket();
+    A.err = p2p_err();
+    return A;
+  }
+  // ... run it as its own kernel (push, raise flags, wait) ...
+  void p2p_run_exchange(const P2PHaloArgs& A) {
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>(32, (A.count + 1023) / 1024));
+    Prof prof(this, K_HALO, 4.0 * 8.0 * (double)A.count); // two messages out, two in
+    p2p_halo_kernel<<<blocks, 256, 0, stream_>>>(A);
+  }
+  // ... and where the received rows of the current epoch live
+  void p2p_my_halos(int slot, const double*& top, const double*& bot) const {
+    const int par = (int)(halo_epoch_[slot] & 1ull);
+    top = p2p_halo(g_.rank, slot, par, 0);
+    bot = p2p_halo(g_.rank, slot, par, 1);
+  }
+  // Halos of the operand field of a marching-kernel pass: with peer memory the exchange is folded into the stencil kernel
+  // itself (ShArgs::push) whenever that kernel is the one that runs; otherwise as halo_ptrs(..., exchange = true).
+  // Call after every other field of A is set; `field` 1: A.x, 2: A.v.
+  void operand_halos(ShArgs& A, int field, int slot) {
+    const double* f = field == 1 ? A.x : A.v;
+    const double*& top = field == 1 ? A.xtop : A.vtop;
+    const double*& bot = field == 1 ? A.xbot : A.vbot;
+    static const bool fuse = !(getenv("JFNK_FUSED_HALO") && atoi(getenv("JFNK_FUSED_HALO")) == 0);
+    if (g_.nranks == 1 || !p2p_ || !fuse) { halo_ptrs(f, slot, true, top, bot); return; }
+    P2PHaloArgs E = p2p_next_exchange(f, slot);
+    p2p_my_halos(slot, top, bot);
+    if (use_tma(A) && aligned16(E.src_first) && aligned16(E.src_last)) { A.push_field = field; A.push = E; }
+    else p2p_run_exchange(E);
   }
 
   bool use_tma(const ShArgs& A) const {
@@ -424,8 +452,8 @@ class CudaOps : public DeviceOps {
 
   void sh_spmv(int which, const double* x, double* y) override {
     ShArgs A = blank();
-    A.x = x; halo_ptrs(x, 2, true, A.xtop, A.xbot);
-    A.out = y;
+    A.x = x; A.out = y;
+    operand_halos(A, 1, 2);
     if (which) sh_launch<OP_L, false>(A); else sh_launch<OP_LAP, false>(A);
   }
   void sh_set_prev(const double* uo, double* d) override {
@@ -455,8 +483,9 @@ class CudaOps : public DeviceOps {
               double* w) override {
     ShArgs A = blank();
     A.x = x0; halo_ptrs(x0, 0, false, A.xtop, A.xbot);
-    A.v = z; halo_ptrs(z, 1, true, A.vtop, A.vbot);
+    A.v = z;
     A.a = sc; A.div = div; A.d = d; A.f0 = f0; A.out = w;
+    operand_halos(A, 2, 1);
     sh_launch<OP_JVP, true>(A);
   }
   void shlin_prepare(const double* U, const double* Uo, double* D, double* b) override {
@@ -727,6 +756,7 @@ class CudaOps : public DeviceOps {
   size_t p2p_off_flags() const { return p2p_off_mail() + sizeof(double) * 2 * kP2PMaxRanks * kP2PMaxScalars; }
   size_t p2p_off_err() const { return p2p_off_flags() + sizeof(unsigned long long) * (kP2PHaloSlots * 2 + kP2PMaxRanks); }
   size_t p2p_bytes() const { return p2p_off_err() + 64; }
+  unsigned* p2p_ticket() const { return reinterpret_cast<unsigned*>(peer_[g_.rank] + p2p_off_err() + 16); }
   double* p2p_halo(int rank, int slot, int par, int dir) const {
     return reinterpret_cast<double*>(peer_[rank]) + p2p_halo_doubles() * (size_t)((slot * 2 + par) * 2 + dir);
   }

@@ -53,7 +53,7 @@ struct P2PHaloArgs {
   const unsigned long long* my_flag_bot; // raised by the next rank
   unsigned long long epoch;
   size_t count;             // doubles per message (2 nx)
-  unsigned* ticket;
+  unsigned* ticket;         // zero between launches
   int* err;
 };
 

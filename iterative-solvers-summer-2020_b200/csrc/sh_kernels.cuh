@@ -22,6 +22,7 @@
 // JVP 40 (x0, z, d, f0 in; w out), linearised matvec 24.
 #pragma once
 #include "cuda_common.cuh"
+#include "p2p_kernels.cuh"
 
 namespace jfnk {
 
@@ -38,6 +39,11 @@ struct ShArgs {
   double* out2;                  // RESID: x + a v (may be null) ; LINPREP: D
   int nx, nrows;
   int norm_off;                  // RESID: S[norm_off..+2] = sum F^2, max|F|, max|t|
+  // Fused halo exchange over peer memory (marching kernel, slab ranks): the kernel itself stores the first / last two rows of
+  // `push_field` (1: x, 2: v) into the neighbours' halo buffers, raises their arrival flags, and its producer lane waits for
+  // this rank's own flags only at the moment it needs a halo row -- the exchange overlaps the interior rows.  0 = off.
+  int push_field;
+  P2PHaloArgs push;
 };
 
 __device__ __forceinline__ const double* sh_row(const double* base, const double* top, const double* bot, int r, int nx,
@@ -132,6 +138,7 @@ __global__ void __launch_bounds__(256) sh_point_kernel(ShArgs A, SHParams P, dou
 constexpr int kTmaTX = 256;        // columns per strip = 2 per consumer thread
 constexpr int kTmaConsumers = 128; // 4 consumer warps
 constexpr int kTmaThreads = kTmaConsumers + 32; // + 1 producer warp (one elected lane issues the copies)
+constexpr int kShPushCtas = 16;    // CTAs that carry the fused halo push (32 KiB each at nx = 16384)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -196,6 +203,30 @@ __global__ void __launch_bounds__(kTmaThreads) sh_tma_kernel(ShArgs A, SHParams 
     for (int s = 0; s < LY::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTmaConsumers / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (A.push_field) {
+    // the first few CTAs push this rank's boundary rows to the ring neighbours (16-byte stores over NVLink); the last of
+    // them to finish raises the neighbours' flags.  Nothing here waits, so every rank always gets to raise its flags.
+    const unsigned npush = min(gridDim.x, (unsigned)kShPushCtas);
+    if (blockIdx.x < npush) {
+      const size_t n2 = A.push.count >> 1; // double2 elements per message
+      const size_t lo = n2 * blockIdx.x / npush, hi = n2 * (blockIdx.x + 1) / npush;
+      const double2* s0 = reinterpret_cast<const double2*>(A.push.src_first);
+      const double2* s1 = reinterpret_cast<const double2*>(A.push.src_last);
+      double2* d0 = reinterpret_cast<double2*>(A.push.dst_prev_bot);
+      double2* d1 = reinterpret_cast<double2*>(A.push.dst_next_top);
+      for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) { d0[i] = s0[i]; d1[i] = s1[i]; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(A.push.ticket, 1u) == npush - 1) {
+          *A.push.ticket = 0u;
+          __threadfence_system();
+          st_release_sys(A.push.flag_prev_bot, A.push.epoch);
+          st_release_sys(A.push.flag_next_top, A.push.epoch);
+        }
+      }
+    }
+  }
   __syncthreads();
 
   ShAcc acc = {0.0, 0.0, 0.0};
@@ -205,6 +236,7 @@ __global__ void __launch_bounds__(kTmaThreads) sh_tma_kernel(ShArgs A, SHParams 
       int s = 0;
       uint32_t ph = 0;
       long long idx = begin;
+      bool top_ok = A.push_field == 0, bot_ok = A.push_field == 0;
       while (idx < end) {
         const int strip = (int)(idx / nrows), r0 = (int)(idx - (long long)strip * nrows);
         const long long run_end = min(end, (long long)(strip + 1) * nrows);
@@ -214,6 +246,17 @@ __global__ void __launch_bounds__(kTmaThreads) sh_tma_kernel(ShArgs A, SHParams 
         for (int ra = r0 - 2; ra < r1 + 2; ++ra) {
           const int y = ra - 2;
           const bool pt = y >= r0;
+          // fused exchange: the neighbours' rows must have arrived before a halo row is fetched
+          if (!top_ok && ra < 0) {
+            wait_flag(A.push.my_flag_top, A.push.epoch, A.push.err);
+            asm volatile("fence.proxy.async;" ::: "memory");
+            top_ok = true;
+          }
+          if (!bot_ok && ra >= nrows) {
+            wait_flag(A.push.my_flag_bot, A.push.epoch, A.push.err);
+            asm volatile("fence.proxy.async;" ::: "memory");
+            bot_ok = true;
+          }
           mbar_wait(&empty[s], ph ^ 1u);
           double* st = stage0 + (size_t)s * LY::kStageDoubles;
           uint32_t bytes = (uint32_t)(W + 4) * 8u * (HAS_V ? 2u : 1u);
