@@ -243,20 +243,21 @@ __global__ void __launch_bounds__(kTmaThreads) sh_tma_kernel(ShArgs A, SHParams 
         const int r1 = r0 + (int)(run_end - idx);
         const int xs = strip * kTmaTX, W = min(kTmaTX, nx - xs);
         const int cl = xs - 2 < 0 ? xs - 2 + nx : xs - 2, cr = xs + W >= nx ? xs + W - nx : xs + W;
+        // fused exchange: the neighbours' rows must have arrived before this run fetches a halo row (checked once per
+        // run, not per row: the producer lane is the pipeline's critical resource)
+        if (!top_ok && r0 < 2) {
+          wait_flag(A.push.my_flag_top, A.push.epoch, A.push.err);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          top_ok = true;
+        }
+        if (!bot_ok && r1 + 2 > nrows) {
+          wait_flag(A.push.my_flag_bot, A.push.epoch, A.push.err);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          bot_ok = true;
+        }
         for (int ra = r0 - 2; ra < r1 + 2; ++ra) {
           const int y = ra - 2;
           const bool pt = y >= r0;
-          // fused exchange: the neighbours' rows must have arrived before a halo row is fetched
-          if (!top_ok && ra < 0) {
-            wait_flag(A.push.my_flag_top, A.push.epoch, A.push.err);
-            asm volatile("fence.proxy.async;" ::: "memory");
-            top_ok = true;
-          }
-          if (!bot_ok && ra >= nrows) {
-            wait_flag(A.push.my_flag_bot, A.push.epoch, A.push.err);
-            asm volatile("fence.proxy.async;" ::: "memory");
-            bot_ok = true;
-          }
           mbar_wait(&empty[s], ph ^ 1u);
           double* st = stage0 + (size_t)s * LY::kStageDoubles;
           uint32_t bytes = (uint32_t)(W + 4) * 8u * (HAS_V ? 2u : 1u);
