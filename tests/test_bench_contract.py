@@ -1,0 +1,35 @@
+"""bench.py's reference arm (`--impl reference`: the oracle = the reference's SciPy path, timed on the host cores) runs
+without a GPU and prints the contract's single JSON line; the product arm refuses to run without a CUDA device."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample-n", "64"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "steps/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("JFNK time-steps/s") and d["value"] > 0 and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["vs_baseline"] is None
+
+
+def test_product_arm_fails_loudly_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        import pytest
+
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stderr + r.stdout) or "no usable CUDA device" in (r.stderr + r.stdout)
