@@ -14,6 +14,8 @@ Outputs (small, committed):
                       2500 steps: its newton_krylov is wrapped to record the result and stop after 3 calls; np.random is
                       seeded so that its `np.random.randn(N**2)` initial state is reproducible) and of sh_linearised.main()
                       (spsolve wrapped the same way)
+    droplet_states.npz  two more of the states the reference ships (INPUTS only): initdrop_rect_1_61-61_100_0.01_... on
+                      [-3,3]^2 and initdrop_coal_1_81-61_100_0.005_... on [-3,5]x[-3,3] (domains read off Q's corner values)
     droplet_init_91x61.npz  droplet.py's initialisers: initialise_coalescing_droplets (4 volume steps), initialise_droplet
                       (3 steps) followed by evolve_R_explicit (until R = 1.07), each with loop_pma relaxations
 """
@@ -157,6 +159,16 @@ def make_droplet_init():
     print("droplet_init_91x61.npz", {k: np.shape(v) for k, v in out.items()}, "R after evolve_R_explicit:", float(out["evolveR_R"]))
 
 
+def make_droplet_states():
+    out = {}
+    for key, name in (("rect61", "initdrop_rect_1_61-61_100_0.01_0.01_0.1_0.15.txt"),
+                      ("coal81", "initdrop_coal_1_81-61_100_0.005_0.01_0.1_0.15.txt")):
+        a = np.loadtxt(os.path.join(REF, name))
+        out[key + "_U"], out[key + "_Q"] = a[:, 0].copy(), a[:, 1].copy()
+    np.savez_compressed(os.path.join(HERE, "droplet_states.npz"), **out)
+    print("droplet_states.npz", {k: v.shape for k, v in out.items()})
+
+
 class _Stop(Exception):
     pass
 
@@ -232,3 +244,4 @@ if __name__ == "__main__":
     make_pma2()
     make_droplet()
     make_droplet_init()
+    make_droplet_states()

@@ -272,3 +272,25 @@ def test_droplet_initialisers_vs_reference_golden(buffers):
     assert rel(Q - Q0, g["evolveR_Q"] - Q0) < 1e-9
     with pytest.raises(ValueError):
         F.compute_U2(Q0, [[0.0, 0.0, -1.0, 1.0]])  # non-positive radius
+
+
+@pytest.mark.parametrize("key,Nx,Ny,endr,eps", [("rect61", 61, 61, 3.0, 0.01), ("coal81", 81, 61, 5.0, 0.005)])
+def test_droplet_step_on_other_shipped_states(buffers, key, Nx, Ny, endr, eps):
+    """The other grid sizes the reference ships states for (61 x 61 on [-3,3]^2, 81 x 61 on [-3,5] x [-3,3]; other precursor
+    film heights): one pass of evolve_with_PDE's loop body (droplet.py:371-384) -- Newton-Krylov with maxiter=20,
+    f_tol=1e-7, then loop_pma(3e-9, 20) -- against the oracle (pinned bit for bit to the reference at 91 x 61)."""
+    g = np.load(os.path.join(GOLD, "droplet_states.npz"))
+    U0, Q0 = g[key + "_U"], g[key + "_Q"]
+    o = DropletOracle(Nx=Nx, Ny=Ny, endl=-3, endr=endr, endb=-3, endt=3, epsilon=eps)
+    o.Q = Q0.copy()
+    hist = []
+    Uref = o.step(U0, 1e-4, dtmesh=3e-9, pmaloops=20, history=hist)
+    F = jf.DropletResidual(Nx=Nx, Ny=Ny, endl=-3.0, endr=endr, endb=-3.0, endt=3.0, epsilon=eps, buffers=buffers)
+    F.set_mesh(Q0)
+    F.set_prev(U0, 1e-4)
+    U = jf.newton_krylov(F, U0, verbose=0, maxiter=20, f_tol=1e-7)
+    assert F.last_history["f_max"][-1] <= 1e-7
+    assert rel(U, Uref) < 1e-8
+    assert F.last_history["nit"] == len(hist[0]["iters"])
+    Q = F.relax_mesh(Q0, U0, 3e-9, loops=20)
+    assert rel(Q - Q0, o.Q - Q0) < 1e-10
