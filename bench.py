@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=16384, help="grid points per side (BASELINE config: 16384)")
-    ap.add_argument("--cpu-sample-n", type=int, default=768, help="grid of the bounded CPU-reference sample")
+    ap.add_argument("--cpu-sample-n", type=int, default=1024, help="grid of the bounded CPU-reference sample")
     ap.add_argument("--gs", default="cgs-ifneeded", choices=["cgs", "cgs-ifneeded", "cgs2"])
     ap.add_argument("--gs-tau", type=float, default=0.25)
     ap.add_argument("--no-cpu-baseline", action="store_true")
