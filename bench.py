@@ -78,6 +78,83 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+FINGERPRINT_FILE = os.path.join(ROOT, "profiles", "sh16384_fingerprint_r2.json")
+N_PROBES = 1024
+
+
+def field_fingerprint(U, N, row0, nrows, world, dist):
+    """P-independent description of the global field held as row slabs: sum, ||.||_2, ||.||_inf and the values at
+    N_PROBES fixed (seeded) grid points.  Computed outside the timed region with torch reductions (a checker, not the
+    product); the slab partials are combined over the ranks, so only the summation order depends on P."""
+    import torch
+
+    acc = torch.stack([U.sum(), (U * U).sum()])
+    linf = U.abs().max().reshape(1)
+    idx = np.sort(np.random.default_rng(4242).integers(0, N * N, N_PROBES))
+    lo, hi = row0 * N, (row0 + nrows) * N
+    mine = (idx >= lo) & (idx < hi)
+    vals = torch.zeros(N_PROBES, dtype=torch.float64, device=U.device)
+    if mine.any():
+        vals[torch.from_numpy(np.nonzero(mine)[0]).to(U.device)] = U[torch.from_numpy(idx[mine] - lo).to(U.device)]
+    if world > 1:
+        dist.all_reduce(acc)
+        dist.all_reduce(vals)
+        dist.all_reduce(linf, op=dist.ReduceOp.MAX)
+    acc = acc.cpu().numpy()
+    return {"sum": float(acc[0]), "l2": float(np.sqrt(acc[1])), "linf": float(linf.item()),
+            "probes": vals.cpu().numpy()}
+
+
+def compare_fingerprint(fp, total_steps, nits, N):
+    """against the single-GPU run of the same code committed in profiles/ (same grid, same number of steps)"""
+    if not os.path.exists(FINGERPRINT_FILE):
+        return None, "no committed single-GPU fingerprint (profiles/sh16384_fingerprint_r2.json)"
+    ref = json.load(open(FINGERPRINT_FILE))
+    ent = ref.get("runs", {}).get(f"{N}:{total_steps}")
+    if ent is None:
+        return None, f"no committed single-GPU entry for grid {N}, {total_steps} steps (have {sorted(ref.get('runs', {}))})"
+    pr = np.asarray(ent["probes"])
+    out = {"rel_l2_probes": float(np.linalg.norm(fp["probes"] - pr) / np.linalg.norm(pr)),
+           "rel_sum": abs(fp["sum"] - ent["sum"]) / abs(ent["sum"]),
+           "rel_l2norm": abs(fp["l2"] - ent["l2"]) / ent["l2"],
+           "rel_linf": abs(fp["linf"] - ent["linf"]) / ent["linf"],
+           "newton_its_equal": list(nits) == list(ent.get("newton_its", [])),
+           "n1_newton_its_sum": int(sum(ent.get("newton_its", []))), "newton_its_sum": int(sum(nits))}
+    out["rel_l2"] = out["rel_l2_probes"]
+    return out, f"vs N=1 entry {N}:{total_steps} of profiles/sh16384_fingerprint_r2.json ({N_PROBES} seeded probe points + norms)"
+
+
+def full_grid_operator_check(F, ctx, U_dev, host_state, N):
+    """One L@u and one Crank-Nicolson residual F(u) at the FULL benchmark size against the oracle's roll stencil
+    (oracle.sh.apply_L_roll_rows / residual_roll_rows, evaluated block of rows by block of rows on the host): exercises
+    the strip / row index arithmetic of the marching kernel and 2 GB vectors where no parity test reaches."""
+    import torch
+    from oracle.sh import apply_L_roll_rows, residual_roll_rows
+
+    t0 = time.perf_counter()
+    y = torch.empty_like(U_dev)
+    ctx.check(ctx.lib.jfnk_spmv_sh(ctx.handle, ctx.buf.ptr(U_dev), ctx.buf.ptr(y)))
+    Lu = y.cpu().numpy().reshape(N, N)
+    u_dev = U_dev * 0.5 + 0.25
+    ctx.check(ctx.lib.jfnk_set_prev(ctx.handle, ctx.buf.ptr(U_dev)))
+    ctx.check(ctx.lib.jfnk_residual(ctx.handle, ctx.buf.ptr(u_dev), ctx.buf.ptr(y)))
+    Fu = y.cpu().numpy().reshape(N, N)
+    u = u_dev.cpu().numpy().reshape(N, N)
+    del y, u_dev
+    Uo = np.asarray(host_state).reshape(N, N)
+    B = 512
+    eL = eF = mL = mF = 0.0
+    for a in range(0, N, B):
+        b = min(N, a + B)
+        r1 = apply_L_roll_rows(Uo, a, b, H, PARAMS["r"])
+        eL, mL = max(eL, float(np.abs(Lu[a:b] - r1).max())), max(mL, float(np.abs(r1).max()))
+        r2 = residual_roll_rows(u, Uo, a, b, H, PARAMS["r"], PARAMS["g"], PARAMS["k"])
+        eF, mF = max(eF, float(np.abs(Fu[a:b] - r2).max())), max(mF, float(np.abs(r2).max()))
+    return {"grid": N, "L_relmax_err": eL / mL, "F_relmax_err": eF / mF, "tolerance": 1e-13,
+            "ok": bool(eL / mL <= 1e-13 and eF / mF <= 1e-13), "seconds": round(time.perf_counter() - t0, 1),
+            "oracle": "oracle.sh.apply_L_roll_rows / residual_roll_rows (np.roll stencil, all rows, 512-row blocks)"}
+
+
 def cpu_reference_sample(n_sample, steps, warmup):
     """The reference's SciPy path (oracle/sh.py = sh_scipy_nk.py:31-61 restated around scipy.optimize.newton_krylov)
     on the host cores, on an n_sample^2 grid with the same h, k, r, g and seeded state; returns seconds/step."""
@@ -143,6 +220,9 @@ def main():
     ap.add_argument("--gs-tau", type=float, default=0.25)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-grid operator check against the roll oracle")
+    ap.add_argument("--write-fingerprint", action="store_true",
+                    help="N=1 only: record this run's field fingerprint in profiles/sh16384_fingerprint_r2.json")
     args = ap.parse_args()
     N = args.grid
 
@@ -172,11 +252,16 @@ def main():
     row0, nrows = F.rows
     n_local = nrows * N
     # synthetic state, independent of the number of ranks (row-wise counter streams), staged in pinned memory
-    host = torch.empty(n_local, dtype=torch.float64).pin_memory()
-    host.numpy()[:] = jf.seeded_slab_state(N, row0, nrows, seed=1234)
+    ctx = F.context()
+    host_np = ctx.buf.pinned_array(n_local)           # page-locked NumPy array (public API)
+    host_np[:] = jf.seeded_slab_state(N, row0, nrows, seed=1234)
+    host = torch.from_numpy(host_np)
     U = host.to("cuda", non_blocking=True)
     torch.cuda.synchronize()
-    ctx = F.context()
+
+    parity = {}
+    if world == 1 and not args.no_parity:
+        parity["full_grid_operators"] = full_grid_operator_check(F, ctx, U, host_np, N)
 
     def barrier():
         if world > 1:
@@ -213,24 +298,57 @@ def main():
     ms = float(t.item())
     value = args.steps / (ms * 1e-3)
 
-    # ---- end-to-end through the public API with HOST buffers: H2D of the state, step, D2H of the result -----
+    # ---- parity evidence, outside the timed region: the field after warmup + timed steps ------------------------
+    total_steps = args.warmup + args.steps
+    nits_all = [int(h["nit"]) for h in hist + thist]
+    fp = field_fingerprint(U, N, row0, nrows, world, dist if world > 1 else None)
+    cmp_, cmp_note = compare_fingerprint(fp, total_steps, nits_all, N)
+    parity["field_after_steps"] = {"steps_taken": total_steps, "sum": fp["sum"], "l2": fp["l2"], "linf": fp["linf"],
+                                   "probe_l2": float(np.linalg.norm(fp["probes"])), "newton_its": nits_all}
+    parity["vs_n1"] = cmp_
+    parity["vs_n1_note"] = cmp_note
+    if cmp_ is not None:
+        parity["rel_l2"] = cmp_["rel_l2"]
+    if args.write_fingerprint and world == 1 and rank == 0:
+        db = json.load(open(FINGERPRINT_FILE)) if os.path.exists(FINGERPRINT_FILE) else {"runs": {}}
+        db["what"] = ("bench.py field fingerprints of single-GPU runs: sum, l2, linf, values at 1024 seeded probe points "
+                      "(default_rng(4242)), Newton iterations per step; key = grid:total_steps (warmup + timed)")
+        db["runs"][f"{N}:{total_steps}"] = {"sum": fp["sum"], "l2": fp["l2"], "linf": fp["linf"],
+                                            "probes": [float(v) for v in fp["probes"]], "newton_its": nits_all}
+        with open(FINGERPRINT_FILE, "w") as f:
+            json.dump(db, f)
+
+    # ---- end-to-end through the PUBLIC API with HOST buffers: U = F.steps(U_host_ndarray, 1) --------------------------
+    # (ndarray in -> host->device copy, set_prev + Newton-Krylov, device->host copy -> ndarray out; the call a user of the
+    #  reference's loop `U = newton_krylov(residual, Uo)` makes per time step)
     e2e = None
     if not args.no_e2e:
+        Uh = host_np
+        host.copy_(U, non_blocking=True)
+        torch.cuda.synchronize()
+        # the two copies alone, to report their bandwidth
+        c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        c0.record(); U.copy_(host, non_blocking=True); c1.record(); host.copy_(U, non_blocking=True); c2.record()
+        torch.cuda.synchronize()
+        h2d_ms, d2h_ms = c0.elapsed_time(c1), c1.elapsed_time(c2)
+        Uh = F.steps(Uh, 1)  # warm the caching host allocator
         barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
+        t0 = time.perf_counter()
         for _ in range(args.steps):
-            U.copy_(host, non_blocking=True)          # pinned host -> device
-            F.steps(U, 1, inplace=True)
-            host.copy_(U, non_blocking=True)          # device -> pinned host (the step's result)
-            torch.cuda.current_stream().synchronize()
-        f1.record()
+            Uh = F.steps(Uh, 1)
+        torch.cuda.synchronize()
+        dt_e2e = time.perf_counter() - t0
         barrier()
-        t2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+        t2 = torch.tensor([dt_e2e], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e = {"value": args.steps / (float(t2.item()) * 1e-3), "unit": "steps/s",
-               "h2d_bytes_per_step": int(8 * N * N), "d2h_bytes_per_step": int(8 * N * N)}
+        nb_ = int(8 * n_local)
+        e2e = {"value": args.steps / float(t2.item()), "unit": "steps/s",
+               "h2d_bytes_per_step": int(8 * N * N), "d2h_bytes_per_step": int(8 * N * N),
+               "call": "U = SHResidual.steps(U_ndarray, 1)  (page-locked NumPy arrays in and out)",
+               "h2d_ms": round(h2d_ms, 2), "d2h_ms": round(d2h_ms, 2),
+               "h2d_GBps": round(nb_ / (h2d_ms * 1e-3) / 1e9, 1), "d2h_GBps": round(nb_ / (d2h_ms * 1e-3) / 1e9, 1)}
+        U = torch.from_numpy(Uh).to("cuda")
 
     # ---- standalone stencil SpMV bandwidth on the same grid (BASELINE metric, config 5 at this size) ---------
     spmv = {}
@@ -299,19 +417,20 @@ def main():
                    "l2": "inputs exceed L2 (2.1 GB per field)" if N >= 8192 else "inputs may fit L2",
                    "newton_its_per_step": nit, "f_evals_per_step": nfev, "arnoldi_its_per_step": inner,
                    "second_gs_passes_per_step": reorth},
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "parity": parity,
+        "kernels": kernels,
         "spmv_GBps": {k: round(v, 1) for k, v in spmv.items()},
         "spmv_frac_of_peak": {k: round(v / (peak * world), 4) for k, v in spmv.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
         ns = args.cpu_sample_n
-        dt, nfev_cpu = cpu_reference_sample(ns, 1, 0)
+        dt, nfev_cpu = cpu_reference_sample(ns, 2, 1)  # one warm-up step, two timed (the GPU arm is timed after warm-up too)
         scale = (N / ns) ** 2
         line["cpu_baseline"] = {
             "value": 1.0 / (dt * scale), "unit": "steps/s", "cores": host_threads(),
             "effective_cores": getattr(cpu_reference_sample, "effective_cores", None), "kind": "port",
-            "sample": (f"oracle/sh.py (SciPy newton_krylov + CSR L@u, the reference's path) 1 step on {ns}^2, same h/k/r/g: "
-                       f"{dt:.2f} s, {nfev_cpu:.0f} F evals; extrapolated linearly in grid points x{scale:.0f} to {N}^2")}
+            "sample": (f"oracle/sh.py (SciPy newton_krylov + CSR L@u, the reference's path) 2 steps after 1 warm-up step on {ns}^2, same h/k/r/g: "
+                       f"{dt:.2f} s/step, {nfev_cpu:.0f} F evals/step; extrapolated linearly in grid points x{scale:.0f} to {N}^2")}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

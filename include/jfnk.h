@@ -124,6 +124,10 @@ size_t jfnk_workspace_bytes(const jfnk_config* cfg);
 int jfnk_create(const jfnk_config* cfg, void* dworkspace, size_t workspace_bytes, jfnk_ctx** out);
 int jfnk_destroy(jfnk_ctx* ctx);
 int jfnk_set_callback(jfnk_ctx* ctx, jfnk_callback cb, void* user);
+/* Callable from inside a jfnk_callback: makes the running jfnk_newton / jfnk_sh_step return JFNK_INVALID right after the
+ * callback returns (the host layer uses it to surface an exception raised by the user's callback, which SciPy would
+ * propagate, _nonlin.py:240-243 -- no exception may cross this ABI). */
+int jfnk_request_stop(jfnk_ctx* ctx);
 /* Preconditioner of the inner LGMRES in jfnk_newton: scipy.optimize.newton_krylov's inner_M (_nonlin.py:1398-1410, :1516),
  * which SciPy hands to lgmres as M, i.e. a LEFT preconditioner (lgmres.py:169 v0 = -psolve(r_outer); _gcrotmk.py:113-121
  * w = lpsolve(matvec(z))).  dout = M din on device vectors of the context's local length; the callee enqueues its work on the

@@ -63,6 +63,7 @@ SIGNATURES = {
     "jfnk_create": (C.c_int, [C.POINTER(Config), _P, C.c_size_t, C.POINTER(_CTX)]),
     "jfnk_destroy": (C.c_int, [_CTX]),
     "jfnk_set_callback": (C.c_int, [_CTX, CALLBACK, C.c_void_p]),
+    "jfnk_request_stop": (C.c_int, [_CTX]),
     "jfnk_set_preconditioner": (C.c_int, [_CTX, PSOLVE, C.c_void_p]),
     "jfnk_comm_unique_id": (C.c_int, [C.c_void_p]),
     "jfnk_comm_init": (C.c_int, [_CTX, C.c_void_p]),

@@ -95,6 +95,12 @@ int jfnk_set_callback(jfnk_ctx* ctx, jfnk_callback cb, void* user) {
   return JFNK_OK;
 }
 
+int jfnk_request_stop(jfnk_ctx* ctx) {
+  JF_CHECK_CTX(ctx);
+  ctx->eng->request_stop();
+  return JFNK_OK;
+}
+
 int jfnk_set_preconditioner(jfnk_ctx* ctx, jfnk_psolve_fn fn, void* user) {
   JF_TRY
   JF_CHECK_CTX(ctx);

@@ -423,7 +423,8 @@ class CudaOps : public DeviceOps {
     Prof prof(this, cls, nb(vecs));
     if (use_tma(A)) {
       using LY = TmaLayout<OP, HAS_V>;
-      static int ctas_per_sm = 0; // per instantiation: opt in to the large dynamic shared memory once
+      // per context (= per device) and per instantiation: opt in to the large dynamic shared memory once
+      int& ctas_per_sm = occupancy_[reinterpret_cast<const void*>(sh_tma_kernel<OP, HAS_V>)];
       if (ctas_per_sm == 0) {
         ck(cudaFuncSetAttribute(sh_tma_kernel<OP, HAS_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LY::kSmemBytes),
            "cudaFuncSetAttribute(smem)");

@@ -127,6 +127,13 @@ int Engine::shlin_step(double* U, double* Uo, int nsteps, double rtol, int maxit
     if (rc) return rc;
     worst = std::max(worst, inf);
     mv += inner;
+    if (inf != 0) {
+      // sh_linearised.py:57 solves with a direct solver; an unconverged LGMRES must not become the next step's state silently
+      if (info) *info = worst;
+      if (matvecs) *matvecs = mv;
+      return fail(JFNK_NO_CONVERGENCE, "jfnk_shlin_step: LGMRES did not reach rtol within maxiter outer cycles (step " +
+                                           std::to_string(s) + ")");
+    }
   }
   if (info) *info = worst;
   if (matvecs) *matvecs = mv;
@@ -527,11 +534,12 @@ int Engine::lgmres_general(const double* b, double* x, double rtol, int maxiter,
     double v0n2, r_norm;
     if (x_is_zero) { v0vec = b; v0n2 = bn2; r_norm = bnorm; }
     else {
-      // r_outer = A x - b ; v0 = -r_outer
-      ops_->mdot(0, nullptr, x, JS_TMP1);
-      ops_->allreduce_sum(JS_TMP1, 1);
-      apply_operator(x, JS_TMP1, FT_, true);
-      ops_->lincomb(FT_, sref(1.0), b, sref(-1.0, -1, JS_TMP1, -1), FT_, JS_TMP2);
+      // r_outer = A x - b ; v0 = -r_outer.  ||x||^2 lives in TMP3: the unfused mesh residuals behind apply_operator park
+      // their (unused) norms in TMP0..TMP2, exactly as Engine::jvp has to allow for.
+      ops_->mdot(0, nullptr, x, JS_TMP3);
+      ops_->allreduce_sum(JS_TMP3, 1);
+      apply_operator(x, JS_TMP3, FT_, true);
+      ops_->lincomb(FT_, sref(1.0), b, sref(-1.0, -1, JS_TMP3, -1), FT_, JS_TMP2);
       ops_->allreduce_sum(JS_TMP2, 1);
       ops_->read_scalars(JS_TMP2, 1, &v0n2);
       r_norm = sqrt(v0n2);
@@ -717,7 +725,16 @@ int Engine::newton(double* u, const jfnk_newton_opts* o, jfnk_history* hist) {
     x0_ = x; f0_ = Fx;
     omega_ = rdiff * std::max(1.0, xmax) / std::max(1.0, fmax);
     if (cfg_.problem == JFNK_PROBLEM_SH) ops_->sh_bind_x0(x0_);
-    if (cb_) cb_(cb_user_, (int32_t)n, x, Fx, fmax, Fx_norm_new);
+    if (cb_) {
+      stop_requested_ = false;
+      cb_(cb_user_, (int32_t)n, x, Fx, fmax, Fx_norm_new);
+      if (stop_requested_) {
+        stop_requested_ = false;
+        if (x != u) ops_->copy(u, x);
+        x0_ = nullptr; f0_ = nullptr;
+        return fail(JFNK_INVALID, "newton_krylov: stopped by the callback");
+      }
+    }
 
     // Eisenstat-Walker forcing (:246-250)
     double eta_A = gamma * (Fx_norm_new * Fx_norm_new) / (Fx_norm * Fx_norm);

@@ -39,6 +39,7 @@ class Engine {
   const std::string& error() const { return err_; }
   void set_callback(jfnk_callback cb, void* user) { cb_ = cb; cb_user_ = user; }
   void set_preconditioner(jfnk_psolve_fn fn, void* user) { psolve_ = fn; psolve_user_ = user; }
+  void request_stop() { stop_requested_ = true; }
 
   // problem setup
   int sh_setup(double h, double r, double g, double k);
@@ -87,6 +88,7 @@ class Engine {
   void* cb_user_ = nullptr;
   jfnk_psolve_fn psolve_ = nullptr; // left preconditioner of the inner solve (inner_M); used by newton() only
   void* psolve_user_ = nullptr;
+  bool stop_requested_ = false;     // set from inside the callback (jfnk_request_stop)
   double* op_tmp_ = nullptr;        // where A z is formed before M is applied (a buffer newton() has free)
 
   // workspace vectors

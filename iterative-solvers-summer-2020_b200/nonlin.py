@@ -86,13 +86,23 @@ def newton_krylov(F, xin, iter=None, rdiff=None, method="lgmres", inner_maxiter=
             inner_M.setup(du, F(du), F)
         ctx.check(ctx.lib.jfnk_set_preconditioner(ctx.handle, ps_c, None))
     cb_c = None
+    cb_err = []
     if callback is not None or m_update is not None:
 
         def _cb(_user, _it, px, pF, _fmax, _fl2):
-            if m_update is not None:
-                m_update(ctx.buf.raw_view(px, n), ctx.buf.raw_view(pF, n))
-            if callback is not None:
-                callback(ctx.buf.view_for_callback(px, n, xin), ctx.buf.view_for_callback(pF, n, xin))
+            # SciPy lets an exception raised by `callback` / `inner_M.update` propagate out of newton_krylov
+            # (_nonlin.py:240-243).  Nothing may cross the C ABI, so it is parked here, the remaining callbacks of the
+            # solve are skipped, and it is re-raised as soon as jfnk_newton returns.
+            if cb_err:
+                return
+            try:
+                if m_update is not None:
+                    m_update(ctx.buf.raw_view(px, n), ctx.buf.raw_view(pF, n))
+                if callback is not None:
+                    callback(ctx.buf.view_for_callback(px, n, xin), ctx.buf.view_for_callback(pF, n, xin))
+            except BaseException as e:  # noqa: BLE001 -- re-raised below
+                cb_err.append(e)
+                ctx.lib.jfnk_request_stop(ctx.handle)
 
         cb_c = _capi.CALLBACK(_cb)
         ctx.check(ctx.lib.jfnk_set_callback(ctx.handle, cb_c, None))
@@ -103,6 +113,8 @@ def newton_krylov(F, xin, iter=None, rdiff=None, method="lgmres", inner_maxiter=
             ctx.lib.jfnk_set_callback(ctx.handle, _capi.CALLBACK(), None)
         if ps_c is not None:
             ctx.lib.jfnk_set_preconditioner(ctx.handle, _capi.PSOLVE(), None)
+    if cb_err:
+        raise cb_err[0]
     if inner_M is not None and ps_err:
         raise ps_err[0]
     h = hist.as_dict()

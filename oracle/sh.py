@@ -150,3 +150,28 @@ def apply_L_roll(u, N, h, r):
     """L u = -Lap(Lap u) - 2 Lap u + (r-1) u by two roll-Laplacians (sh_scipy_nk.py:39 without the matrix)."""
     lu = apply_lap_roll(u, N, h)
     return -apply_lap_roll(lu, N, h) - 2 * lu + (r - 1) * np.asarray(u).reshape(-1)
+
+
+def apply_L_roll_rows(U2d, a, b, h, r):
+    """Rows [a, b) of L u for an N x N periodic field given as a 2-D array, by the same two roll-Laplacians as
+    :func:`apply_L_roll` (bit-identical to its rows a..b-1, tests/test_oracle.py) but touching only rows a-2 .. b+1:
+    lets bench.py check the engine at 16384^2, where the full-field rolls would need ~30 GB of temporaries."""
+    N = U2d.shape[0]
+    e = 1 / h**2
+    blk = U2d[np.arange(a - 2, b + 2) % N]
+
+    def lap_rows(B):  # 5-point Laplacian of the interior rows of B (periodic in columns, rows from the block itself)
+        # same operand order as apply_lap_roll: e*(up + down + left + right) - 4 e u
+        return e * (B[:-2] + B[2:] + np.roll(B[1:-1], 1, 1) + np.roll(B[1:-1], -1, 1)) - 4 * e * B[1:-1]
+
+    l1 = lap_rows(blk)          # rows a-1 .. b
+    l2 = lap_rows(l1)           # rows a .. b-1
+    return -l2 - 2 * l1[1:-1] + (r - 1) * blk[2:-2]
+
+
+def residual_roll_rows(U2d, Uo2d, a, b, h, r, g, k):
+    """Rows [a, b) of the Crank-Nicolson residual of sh_scipy_nk.py:47-49 with L applied by :func:`apply_L_roll_rows`."""
+    u, uo = U2d[a:b], Uo2d[a:b]
+    uu, uouo = np.multiply(u, u), np.multiply(uo, uo)
+    return (u - uo) / k - (apply_L_roll_rows(U2d, a, b, h, r) + g * uu - np.multiply(u, uu)
+                           + apply_L_roll_rows(Uo2d, a, b, h, r) + g * uouo - np.multiply(uo, uouo)) / 2

@@ -5,14 +5,17 @@
 Three runs advance side by side, each with its own state (solution U, mesh potential Q):
   * the pure oracle (SciPy + scipy.fft), which also owns the reference time-step sequence dt_n = 1e-4 * scale;
   * engine run "lockstep": fed the oracle's dt_n each step -- the hot path (Newton-Krylov step + mesh relaxation)
-    under identical inputs.  Bar: 1e-8 relative L2 (north_star) for the first 30 steps as long as both sides take
-    the same number of Newton iterations; 2e-7 after a termination flip at the f_tol = 1e-7 threshold or beyond
-    step 30 (10x the reference's own sensitivity to a 1e-14 perturbation of its initial state,
-    profiles/droplet_oracle_sensitivity_r1.txt);
+    under identical inputs.  Bar: 1e-8 relative L2 (north_star) on every step until the first termination flip (the
+    two sides take a different number of Newton iterations because the last iterate sits at the f_tol = 1e-7
+    threshold); after a flip the two runs are on different, equally converged branches and the WORST value over the
+    whole run must stay below 3e-8 (the reference itself moves by 1.8e-8 under a 1e-14 perturbation of its initial
+    state, profiles/droplet_oracle_sensitivity_r1.txt).  The worst value and the number of flips are printed;
   * engine run "free": computes its own scale += exp(-10 ||dU||).  The adaptive step feeds every field difference
     back into dt (a 1e-9 field difference moves dt by ~1e-7), so this run is held to 1e-7 / 1e-6 and its deviation is
-    reported.  JFNK_DROPLET_STEPS (default 6; config 2 is 100) sets
-the length; the 100-step results of this round are recorded in profiles/droplet_100steps_r1.json."""
+    reported.
+Length: BASELINE config 2 is 100 steps, and that is what runs on the GPU (`-m gpu`, about a minute, most of it the
+SciPy side).  The CPU test double of the host-logic suite runs 6 steps (it is ~100x slower than the B200);
+JFNK_DROPLET_STEPS overrides both."""
 import json
 import os
 import time
@@ -26,7 +29,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def test_droplet_coalescence_run(buffers):
-    nsteps = int(os.environ.get("JFNK_DROPLET_STEPS", "6"))
+    nsteps = int(os.environ.get("JFNK_DROPLET_STEPS", "100" if buffers.name == "cuda" else "6"))
     pmaloops = int(os.environ.get("JFNK_DROPLET_PMALOOPS", "400"))
     g = np.load(os.path.join(GOLD, "droplet_91x61.npz"))
     ref = DropletOracle()  # the reference path end to end
@@ -83,7 +86,7 @@ def test_droplet_coalescence_run(buffers):
                 r["flipped"] = True
                 r["flips"] += 1
             if name == "lockstep":
-                assert err < (1e-8 if (s < 30 and not r["flipped"]) else 2e-7), (name, s, err)
+                assert err < (1e-8 if not r["flipped"] else 3e-8), (name, s, err, r["flips"])
             else:
                 assert err < (1e-7 if s < 30 else 1e-6), (name, s, err)
             assert errq < 1e-8, (name, s, errq)

@@ -294,3 +294,75 @@ def test_droplet_step_on_other_shipped_states(buffers, key, Nx, Ny, endr, eps):
     assert F.last_history["nit"] == len(hist[0]["iters"])
     Q = F.relax_mesh(Q0, U0, 3e-9, loops=20)
     assert rel(Q - Q0, o.Q - Q0) < 1e-10
+
+
+def _rect_state(Nx, Ny, endl, endr, endb, endt, eps=0.01):
+    """A smooth droplet-like state on a mildly deformed mesh of a grid whose two spacings DIFFER."""
+    ksi, eta = np.meshgrid(np.linspace(endl, endr, Nx), np.linspace(endb, endt, Ny))
+    Q = 0.5 * ksi ** 2 + 0.5 * eta ** 2 + 0.05 * np.cos(np.pi * (ksi - endl) / (endr - endl)) * np.cos(np.pi * (eta - endb) / (endt - endb))
+    U = eps + 0.8 * np.exp(-((ksi - 1.0) ** 2 + eta ** 2) / 0.8) + 0.5 * np.exp(-((ksi - 3.0) ** 2 + (eta - 0.3) ** 2) / 0.5)
+    return U.reshape(-1), Q.reshape(-1)
+
+
+def test_rectangular_spacing_dksi_differs_from_deta(buffers):
+    """Every shipped grid has dksi == deta == 0.1, so nothing above tells dksi^2, deta^2 and the dksi*deta divisor of
+    M.Leig (droplet.py:831-833, reference quirk 3) apart.  91 x 41 on [-3,6] x [-3,3] has dksi = 0.1, deta = 0.15:
+    Laplace_operator, the droplet residual, a Newton-Krylov step and the DCT mesh relaxation against the oracle."""
+    Nx, Ny, box = 91, 41, (-3.0, 6.0, -3.0, 3.0)
+    U, Q = _rect_state(Nx, Ny, *box)
+    o = DropletOracle(Nx=Nx, Ny=Ny, endl=box[0], endr=box[1], endb=box[2], endt=box[3])
+    assert abs(o.ops.dksi - 0.1) < 1e-15 and abs(o.ops.deta - 0.15) < 1e-15
+    F = jf.DropletResidual(Nx=Nx, Ny=Ny, endl=box[0], endr=box[1], endb=box[2], endt=box[3], buffers=buffers)
+    o.set_mesh(Q)
+    F.set_mesh(Q)
+    vxx, vyy = F.laplace(U)
+    rxx, ryy = o.ops.laplace_of(U, o.met)
+    assert relmax(vxx, rxx) < 1e-11 and relmax(vyy, ryy) < 1e-11
+    o.set_prev(U, 1e-4)
+    F.set_prev(U, 1e-4)
+    u = U * (1 + 1e-3 * np.sin(np.arange(Nx * Ny)))
+    assert relmax(F(u), o.residual(u)) < 1e-10
+    # mesh relaxation: the spectral divide uses Leig = lam/(dksi*deta); with dksi^2 or deta^2 the increment is off by 50 %
+    o.loop_pma(3e-9, 5)
+    Qn = F.relax_mesh(Q, U, 3e-9, loops=5)
+    assert rel(Qn - Q, o.Q - Q) < 1e-10
+    wrong = DropletOracle(Nx=Nx, Ny=Ny, endl=box[0], endr=box[1], endb=box[2], endt=box[3])
+    wrong.ops.Leig = wrong.ops.Leig * (wrong.ops.dksi * wrong.ops.deta) / wrong.ops.dksi ** 2
+    wrong.set_mesh(Q)
+    wrong.set_prev(U, 1e-4)
+    wrong.loop_pma(3e-9, 5)
+    assert rel(Qn - Q, wrong.Q - Q) > 1e-3  # the test does discriminate the divisor
+
+
+@pytest.mark.parametrize("model", ["pma2", "droplet"])
+def test_lgmres_restarts_on_mesh_problems(buffers, model):
+    """scipy.sparse.linalg.lgmres with maxiter > 1 (outer restarts: r = b - A x needs ||x|| kept across an operator
+    application whose unfused mesh residual kernels park their norms in the scratch scalars) on the FD Jacobian of the
+    moving-mesh residuals, against SciPy on the oracle's KrylovJacobian."""
+    from scipy.optimize._nonlin import KrylovJacobian
+    from scipy.sparse.linalg import lgmres
+
+    if model == "pma2":
+        g = np.load(os.path.join(GOLD, "pma2_n51.npz"))
+        o, F = PMA2Oracle(N=51), jf.PMA2Residual(N=51, buffers=buffers, inner_m=10, outer_k=2)
+        o.set_mesh(g["op_Q"]); F.set_mesh(g["op_Q"])
+        o.set_prev(g["op_Uval"]); F.set_prev(g["op_Uval"])
+        x0 = g["op_u"]
+    else:
+        g = np.load(os.path.join(GOLD, "droplet_91x61.npz"))
+        o, F = DropletOracle(), jf.DropletResidual(buffers=buffers, inner_m=10, outer_k=2)
+        o.set_mesh(g["state_Q"]); F.set_mesh(g["state_Q"])
+        o.set_prev(g["state_U"], 1e-4); F.set_prev(g["state_U"], 1e-4)
+        x0 = g["state_U"]
+    jac = KrylovJacobian()
+    b = o.residual(x0)
+    jac.setup(x0.copy(), b, o.residual)
+    F.linearize(x0)
+    # a short Arnoldi length forces several outer cycles (the FD noise floor of these operators is ~6e-5 relative)
+    xs, info_s = lgmres(jac.op, b, rtol=1e-4, atol=0, maxiter=40, inner_m=10, outer_k=2)
+    xg, info_g = F.lgmres(b, rtol=1e-4, maxiter=40)
+    assert info_s == 0 and info_g == 0
+    assert F.last_lgmres["inner"] > 12  # more than one cycle was needed
+    r = b - jac.matvec(xg)
+    assert np.linalg.norm(r) <= 2e-4 * np.linalg.norm(b)
+    assert rel(xg, xs) < 1e-2

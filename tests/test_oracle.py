@@ -121,3 +121,20 @@ def test_sh_oracle_matches_reference_script_golden():
     for s in (1, 2, 3):
         U, Uo = ol.step(U, Uo)
         assert np.array_equal(U, g[f"lin_U{s}"]), s
+
+
+def test_block_row_roll_operator_is_the_full_roll_operator():
+    """apply_L_roll_rows / residual_roll_rows (used by bench.py to check the engine at 16384^2 block by block) are the
+    rows of apply_L_roll / SHOracle.residual -- bit for bit for L, rounding-close to the CSR residual."""
+    from oracle.sh import apply_L_roll_rows, residual_roll_rows
+
+    N = 48
+    o = SHOracle(N=N, d=30.0)
+    u, uo = seeded_state(N, 3), seeded_state(N, 4)
+    full = apply_L_roll(u, N, o.h, o.r).reshape(N, N)
+    for a, b in ((0, 5), (3, 17), (40, 48), (0, 48)):
+        assert np.array_equal(apply_L_roll_rows(u.reshape(N, N), a, b, o.h, o.r), full[a:b])
+    o.set_prev(uo)
+    ref = o.residual(u).reshape(N, N)
+    got = residual_roll_rows(u.reshape(N, N), uo.reshape(N, N), 0, N, o.h, o.r, o.g, o.k)
+    assert relmax(got, ref) < 1e-13

@@ -363,3 +363,59 @@ def test_engine_vs_reference_script_golden(buffers):
     for s in (1, 2, 3):
         U, Uo = FL.steps(U, Uo, nsteps=1)
         assert rel(U, g[f"lin_U{s}"]) < 1e-10, s
+
+
+@pytest.mark.parametrize("kw", [dict(x_tol=1e-6), dict(x_rtol=1e-7), dict(f_rtol=1e-4), dict(f_tol=1e-3, x_tol=1e-5),
+                                dict(f_tol=1e-9, f_rtol=1e-6, x_rtol=1e-9)])
+def test_termination_conditions_match_scipy(buffers, kw):
+    """TerminationCondition (scipy/optimize/_nonlin.py:328-385) beyond the default f_tol: x_tol / x_rtol compare
+    |dx|_inf with |x|_inf, f_rtol compares |F|_inf with the first |F|_inf; unset entries are inf.  Same number of
+    Newton iterations and the same field as SciPy with the same keywords."""
+    from scipy.optimize import newton_krylov as scipy_nk
+
+    N = 64
+    o = SHOracle(N=N)
+    F = jf.SHResidual(N=N, buffers=buffers)
+    Uo = seeded_state(N)
+    o.set_prev(Uo)
+    F.set_prev(Uo)
+    hist = []
+    ref = scipy_nk(o.residual, Uo, callback=lambda x, f: hist.append(np.abs(f).max()), **kw)
+    got = jf.newton_krylov(F, Uo, **kw)
+    assert F.last_history["nit"] == len(hist)
+    assert rel(got, ref) < 1e-8
+
+
+def test_linearised_step_reports_an_unconverged_solve(buffers):
+    """sh_linearised.py:57 solves exactly (spsolve); the matrix-free LGMRES replacement must not hand back an
+    unconverged field silently."""
+    N = 48
+    S = jf.SHLinearised(N=N, d=30.0, buffers=buffers)
+    U = seeded_state(N, 4)
+    with pytest.raises(jf.NoConvergence):
+        S.steps(U, nsteps=1, rtol=1e-13, maxiter=1)
+    Un, _ = S.steps(U, nsteps=1)
+    assert S.last_info["info"] == 0
+
+
+def test_callback_exception_propagates_like_scipy(buffers):
+    """SciPy lets an exception raised inside `callback` leave newton_krylov (_nonlin.py:240-243); ctypes would print and
+    swallow it.  The host layer parks it, stops the solve and re-raises."""
+    N = 64
+    F = jf.SHResidual(N=N, buffers=buffers)
+    Uo = seeded_state(N)
+    F.set_prev(Uo)
+    calls = []
+
+    class Boom(RuntimeError):
+        pass
+
+    def cb(x, f):
+        calls.append(1)
+        raise Boom("from the callback")
+
+    with pytest.raises(Boom):
+        jf.newton_krylov(F, Uo, callback=cb)
+    assert len(calls) == 1  # the solve stopped at once
+    # the context is still usable afterwards
+    assert rel(jf.newton_krylov(F, Uo), jf.newton_krylov(F, Uo)) == 0.0
