@@ -7,6 +7,7 @@
 #include <string.h>
 #include <algorithm>
 #include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -19,6 +20,7 @@
 #include "nccl_dl.h"
 #include "p2p_kernels.cuh"
 #include "sh_kernels.cuh"
+#include "sh_box_kernel.cuh"
 
 namespace jfnk {
 
@@ -50,10 +52,22 @@ class CudaOps : public DeviceOps {
     if (!ck(cudaMemsetAsync(ws_.ticket, 0, sizeof(unsigned), stream_), "cudaMemset(ticket)")) { why = err_; return; }
     if (!ck(cudaMallocHost(&pinned_, sizeof(double) * (JS_COUNT + 1)), "cudaMallocHost")) { why = err_; return; }
     if (g_.nranks > 1) {
-      // row halos of the linearisation point (x0), of the operand vector (z / dx) and of a generic field
+      // row halos of the linearisation point (x0), of the operand vector (z / dx) and of a generic field; the top and the
+      // bottom pair of a slot are adjacent (4 rows) so that one tensor map describes both (sh_box_kernel)
       size_t hb = sizeof(double) * 2 * (size_t)g_.nx;
-      for (int i = 0; i < 6; ++i)
-        if (!ck(cudaMalloc(&halo_[i], hb), "cudaMalloc(halo)")) { why = err_; return; }
+      for (int i = 0; i < 3; ++i) {
+        if (!ck(cudaMalloc(&halo_[2 * i], 2 * hb), "cudaMalloc(halo)")) { why = err_; return; }
+        halo_[2 * i + 1] = halo_[2 * i] + 2 * (size_t)g_.nx;
+      }
+    }
+    {
+      // cuTensorMapEncodeTiled through the runtime (the library links cudart statically and never libcuda)
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+          qres == cudaDriverEntryPointSuccess)
+        encode_ = reinterpret_cast<EncodeFn>(fn);
+      cudaGetLastError();
     }
     ok = true;
   }
@@ -64,7 +78,7 @@ class CudaOps : public DeviceOps {
     if (comm_ && nccl_) nccl_->CommDestroy(comm_);
     for (auto& r : recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : free_events_) cudaEventDestroy(e);
-    for (int i = 0; i < 6; ++i) if (halo_[i]) cudaFree(halo_[i]);
+    for (int i = 0; i < 6; i += 2) if (halo_[i]) cudaFree(halo_[i]);
     if (dtab_) cudaFree(dtab_);
     if (dctx_) cudaFree(dctx_);
     if (dcty_) cudaFree(dcty_);
@@ -401,8 +415,92 @@ class CudaOps : public DeviceOps {
     else p2p_run_exchange(E);
   }
 
+  // ---- tensor-map TMA (sh_box_kernel) ------------------------------------------------------------------
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  // (boxw x 2) boxes over `rows` rows of nx doubles starting at base; encoded once per (base, rows, boxw) -- the vectors
+  // of a context live in one fixed workspace, so the cache stays small
+  bool box_map(CUtensorMap* out, const double* base, int rows, int boxw) {
+    auto key = std::make_tuple((const void*)base, rows, boxw);
+    auto it = maps_.find(key);
+    if (it != maps_.end()) { *out = it->second; return true; }
+    cuuint64_t dims[2] = {(cuuint64_t)g_.nx, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)g_.nx * 8};
+    cuuint32_t box[2] = {(cuuint32_t)boxw, (cuuint32_t)kBoxR};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = encode_(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         // the 16-byte rows of a halo-column box must not be promoted to 256-byte L2 fetches (measured: +9 % DRAM reads)
+                         boxw >= 32 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    if (maps_.size() > 4096) maps_.clear();
+    maps_[key] = m;
+    *out = m;
+    return true;
+  }
+  // the halo rows of a field as (base of a row-pair array, row of the top pair, row of the bottom pair): the slab itself on
+  // one rank (periodic wrap), else the 4-row halo buffer (top pair then bottom pair, adjacent)
+  bool halo_layout(const double* f, const double* top, const double* bot, const double*& base, int& rows, int& rtop,
+                   int& rbot) const {
+    if (top == f + (size_t)(g_.nrows - 2) * g_.nx && bot == f) { base = f; rows = g_.nrows; rtop = g_.nrows - 2; rbot = 0; return true; }
+    if (bot == top + 2 * (size_t)g_.nx) { base = top; rows = 4; rtop = 0; rbot = 2; return true; }
+    return false;
+  }
+  bool use_box(const ShArgs& A) const {
+    if (!encode_ || (variant_ != 0 && variant_ != 3)) return false;
+    static const bool off = getenv("JFNK_BOX") && atoi(getenv("JFNK_BOX")) == 0;
+    if (off && variant_ == 0) return false;
+    if ((g_.nx % 2) || (g_.nrows % kBoxR) || g_.nrows < 4) return false;
+    if (variant_ == 0 && (g_.nx < kBoxStrip || g_.nrows < 32)) return false;
+    if (variant_ == 3 && g_.nx < kBoxW) return false;
+    return aligned16(A.x) && aligned16(A.xtop) && aligned16(A.xbot) && aligned16(A.out) &&
+           (!A.v || (aligned16(A.v) && aligned16(A.vtop) && aligned16(A.vbot))) && (!A.d || aligned16(A.d)) &&
+           (!A.f0 || aligned16(A.f0)) && (!A.out2 || aligned16(A.out2));
+  }
+  template <int OP, bool HAS_V>
+  bool box_launch(const ShArgs& A) {
+    using LY = BoxLayout<OP, HAS_V>;
+    ShBoxMaps M;
+    ShBoxRows hr = {0, 0, 0, 0};
+    memset(&M, 0, sizeof(M));
+    const double* hb; int hrows;
+    if (!halo_layout(A.x, A.xtop, A.xbot, hb, hrows, hr.x_top, hr.x_bot)) return false;
+    if (!box_map(&M.x_main, A.x, g_.nrows, kBoxW) || !box_map(&M.xc_main, A.x, g_.nrows, 2) ||
+        !box_map(&M.x_halo, hb, hrows, kBoxW) || !box_map(&M.xc_halo, hb, hrows, 2)) return false;
+    if (HAS_V) {
+      if (!halo_layout(A.v, A.vtop, A.vbot, hb, hrows, hr.v_top, hr.v_bot)) return false;
+      if (!box_map(&M.v_main, A.v, g_.nrows, kBoxW) || !box_map(&M.vc_main, A.v, g_.nrows, 2) ||
+          !box_map(&M.v_halo, hb, hrows, kBoxW) || !box_map(&M.vc_halo, hb, hrows, 2)) return false;
+    }
+    if (LY::kHasD && !box_map(&M.d, A.d, g_.nrows, kBoxW)) return false;
+    if (LY::kHasF && !box_map(&M.f0, A.f0, g_.nrows, kBoxW)) return false;
+    int& ctas_per_sm = occupancy_[reinterpret_cast<const void*>(sh_box_kernel<OP, HAS_V>)];
+    if (ctas_per_sm == 0) {
+      ck(cudaFuncSetAttribute(sh_box_kernel<OP, HAS_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LY::kSmemBytes),
+         "cudaFuncSetAttribute(box smem)");
+      int nb_ = 0;
+      ck(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, sh_box_kernel<OP, HAS_V>, kBoxThreads, LY::kSmemBytes),
+         "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+      ctas_per_sm = nb_ > 0 ? nb_ : 1;
+    }
+    // persistent grid: every CTA resident, each owning an equal contiguous range of (strip, row pair) units (>= 8 pairs)
+    long long total = (long long)((g_.nx + kBoxStrip - 1) / kBoxStrip) * (g_.nrows / kBoxR);
+    long long blocks = std::min<long long>((long long)sms_ * ctas_per_sm, std::max<long long>(1, total / 8));
+    if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+    sh_box_kernel<OP, HAS_V><<<(int)blocks, kBoxThreads, LY::kSmemBytes, stream_>>>(M, A, hr, shp_, S_, ws_);
+    return true;
+  }
+
   bool use_tma(const ShArgs& A) const {
     if (variant_ == 1) return false;
+    if (use_box(A)) return true; // (the fused halo push exists in both marching kernels)
+    return tma_ok(A);
+  }
+  bool tma_ok(const ShArgs& A) const {
+    if (variant_ == 1 || variant_ == 3) return false;
     bool ok = (g_.nx % 2 == 0) && aligned16(A.x) && aligned16(A.xtop) && aligned16(A.xbot) && aligned16(A.out) &&
               (!A.v || (aligned16(A.v) && aligned16(A.vtop) && aligned16(A.vbot))) && (!A.d || aligned16(A.d)) &&
               (!A.f0 || aligned16(A.f0)) && (!A.out2 || aligned16(A.out2));
@@ -416,12 +514,20 @@ class CudaOps : public DeviceOps {
     A.nx = g_.nx; A.nrows = g_.nrows;
     // algorithmic traffic in vectors of 8 B/point: inputs read once + outputs written once
     const int cls = OP == OP_LAP ? K_SPMV_LAP : OP == OP_L ? K_SPMV_L : OP == OP_SETPREV ? K_SET_PREV
-                  : OP == OP_RESID ? K_RESIDUAL : OP == OP_JVP ? K_JVP : K_SHLIN;
+                  : OP == OP_RESID ? K_RESIDUAL : (OP == OP_JVP || OP == OP_JVPG) ? K_JVP : K_SHLIN;
     const double vecs = OP == OP_LAP || OP == OP_L || OP == OP_SETPREV ? 2.0
-                      : OP == OP_RESID ? (3.0 + (HAS_V ? 1.0 : 0.0) + (A.out2 ? 1.0 : 0.0))
-                      : OP == OP_JVP ? 5.0 : OP == OP_LINPREP ? 4.0 : 3.0;
+                      : OP == OP_RESID ? (3.0 + (HAS_V ? 1.0 : 0.0) + (A.out2 ? 1.0 : 0.0) + (A.out3 ? 1.0 : 0.0))
+                      : OP == OP_JVP ? 5.0 : OP == OP_JVPG ? 4.0 : OP == OP_LINPREP ? 4.0 : 3.0;
     Prof prof(this, cls, nb(vecs));
-    if (use_tma(A)) {
+    if (use_box(A) && box_launch<OP, HAS_V>(A)) return;
+    if (variant_ == 3 || !tma_ok(A)) {
+      // (a push folded into the arguments needs a marching kernel: operand_halos() only does that when use_tma() held,
+      //  and box_launch can only decline for a halo layout no caller produces)
+      int blocks = stream_grid(g_.n(), 256);
+      sh_point_kernel<OP, HAS_V><<<blocks, 256, 0, stream_>>>(A, shp_, S_, ws_);
+      return;
+    }
+    {
       using LY = TmaLayout<OP, HAS_V>;
       // per context (= per device) and per instantiation: opt in to the large dynamic shared memory once
       int& ctas_per_sm = occupancy_[reinterpret_cast<const void*>(sh_tma_kernel<OP, HAS_V>)];
@@ -438,9 +544,6 @@ class CudaOps : public DeviceOps {
       long long blocks = std::min<long long>((long long)sms_ * ctas_per_sm, std::max<long long>(1, total / 16));
       if (blocks > kMaxBlocks) blocks = kMaxBlocks;
       sh_tma_kernel<OP, HAS_V><<<(int)blocks, kTmaThreads, LY::kSmemBytes, stream_>>>(A, shp_, S_, ws_);
-    } else {
-      int blocks = stream_grid(g_.n(), 256);
-      sh_point_kernel<OP, HAS_V><<<blocks, 256, 0, stream_>>>(A, shp_, S_, ws_);
     }
   }
 
@@ -464,10 +567,10 @@ class CudaOps : public DeviceOps {
     sh_launch<OP_SETPREV, false>(A);
   }
   void sh_residual(const double* x, const double* v, ScalarRef a, const double* d, double* xt_out, double* F,
-                   int norm_off) override {
+                   double* g_out, int norm_off) override {
     ShArgs A = blank();
     A.x = x; halo_ptrs(x, 2, true, A.xtop, A.xbot);
-    A.d = d; A.out = F; A.out2 = xt_out; A.norm_off = norm_off;
+    A.d = d; A.out = F; A.out2 = xt_out; A.out3 = g_out; A.norm_off = norm_off;
     if (v) {
       A.v = v; halo_ptrs(v, 1, true, A.vtop, A.vbot);
       A.a = a;
@@ -481,13 +584,14 @@ class CudaOps : public DeviceOps {
     halo_ptrs(x0, 0, true, t, b);
   }
   void sh_jvp(const double* x0, const double* z, ScalarRef sc, ScalarRef div, const double* d, const double* f0,
-              double* w) override {
+              const double* g0, double* w) override {
     ShArgs A = blank();
     A.x = x0; halo_ptrs(x0, 0, false, A.xtop, A.xbot);
     A.v = z;
-    A.a = sc; A.div = div; A.d = d; A.f0 = f0; A.out = w;
+    A.a = sc; A.div = div; A.out = w;
+    if (g0) A.d = g0; else { A.d = d; A.f0 = f0; }
     operand_halos(A, 2, 1);
-    sh_launch<OP_JVP, true>(A);
+    if (g0) sh_launch<OP_JVPG, true>(A); else sh_launch<OP_JVP, true>(A);
   }
   void shlin_prepare(const double* U, const double* Uo, double* D, double* b) override {
     ShArgs A = blank();
@@ -862,6 +966,8 @@ class CudaOps : public DeviceOps {
   ReduceWs ws_ = {nullptr, nullptr};
   double* halo_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::map<const void*, int> occupancy_;
+  EncodeFn encode_ = nullptr;
+  std::map<std::tuple<const void*, int, int>, CUtensorMap> maps_;
   MeshTables* dtab_ = nullptr;
   bool tab_valid_ = false;
   MeshParams last_mp_ = {1.0, 1.0, 0, 0, 0, 0};

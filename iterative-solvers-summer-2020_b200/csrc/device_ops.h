@@ -119,13 +119,15 @@ class DeviceOps {
   virtual void sh_set_prev(const double* uo, double* d) = 0;       // d = Uo/k + N(Uo)/2
   // t = x + a v (v may be null) ; F = G(t) - d ; xt_out (may be null) = t ;
   // S[norm_off+0] = sum F^2, S[norm_off+1] = max|F|, S[norm_off+2] = max|t|  (local partials; caller all-reduces)
+  // g_out (may be null) = G(t) = F + d, the part of the residual that depends on t: kept for the accepted iterate so that
+  // the Jacobian-vector products read ONE pointwise operand, G(x0), instead of d and f0
   virtual void sh_residual(const double* x, const double* v, ScalarRef a, const double* d, double* xt_out, double* F,
-                           int norm_off) = 0;
+                           double* g_out, int norm_off) = 0;
   // cache the row halos of the linearisation point (multi-rank); no-op on one rank
   virtual void sh_bind_x0(const double* x0) = 0;
-  // w = (G(x0 + sc z) - d - f0)/div
+  // w = (G(x0 + sc z) - d - f0)/div ; with g0 = G(x0) given: w = (G(x0 + sc z) - g0)/div (d, f0 unused)
   virtual void sh_jvp(const double* x0, const double* z, ScalarRef sc, ScalarRef div, const double* d, const double* f0,
-                      double* w) = 0;
+                      const double* g0, double* w) = 0;
   // linearly-implicit SH: D = (5U-Uo)^2 k/16 - g k U ; b = U + k/2 L U
   virtual void shlin_prepare(const double* U, const double* Uo, double* D, double* b) = 0;
   // w = a (z + D z - k/2 L z)

@@ -42,6 +42,7 @@ size_t Engine::vector_stride(const jfnk_config& c) {
 
 int Engine::vector_count(const jfnk_config& c) {
   int cnt = 4;                        // XT, FX, FT, D
+  if (c.problem == JFNK_PROBLEM_SH) cnt += 2; // GX, GT: G = F + d of the current iterate / of the line-search trial
   cnt += c.inner_m + c.outer_k;       // Arnoldi slots 1..m
   cnt += c.outer_k + 1;               // augmentation ring
   if (is_mesh_problem(c.problem)) cnt += kNumScratch + 7 + 2; // scratch, metric fields, UVAL, CN
@@ -58,6 +59,8 @@ Engine::Engine(const jfnk_config& cfg, DeviceOps* ops, double* ws, size_t /*ws_d
   size_t i = 0;
   auto next = [&]() { return ws_ + vstride_ * (i++); };
   XT_ = next(); FX_ = next(); FT_ = next(); D_ = next();
+  GX_ = GT_ = nullptr;
+  if (cfg.problem == JFNK_PROBLEM_SH) { GX_ = next(); GT_ = next(); }
   for (int j = 0; j < cfg.inner_m + cfg.outer_k; ++j) VS_.push_back(next());
   for (int j = 0; j < cfg.outer_k + 1; ++j) OV_.push_back(next());
   if (is_mesh_problem(cfg.problem)) {
@@ -315,10 +318,10 @@ void Engine::generic_residual(const double* u, double* F, int norm_off) {
   }
 }
 
-int Engine::eval_residual(const double* x, const double* v, ScalarRef a, double* xt_out, double* F, int norm_off,
-                          double nrm[3]) {
+int Engine::eval_residual(const double* x, const double* v, ScalarRef a, double* xt_out, double* F, double* g_out,
+                          int norm_off, double nrm[3]) {
   if (cfg_.problem == JFNK_PROBLEM_SH) {
-    ops_->sh_residual(x, v, a, D_, xt_out, F, norm_off);
+    ops_->sh_residual(x, v, a, D_, xt_out, F, g_out, norm_off);
   } else if (cfg_.problem == JFNK_PROBLEM_PMA2) {
     // t = x + a v is formed inside the evaluation (never stored unless the caller wants the trial iterate)
     if (!v && xt_out && xt_out != x) ops_->copy(xt_out, x);
@@ -347,7 +350,7 @@ int Engine::residual(const double* u, double* F) {
   if (cfg_.problem == JFNK_PROBLEM_SH_LINEAR) return fail(JFNK_INVALID, "jfnk_residual: not defined for SH_LINEAR");
   if (!problem_ready(why)) return fail(JFNK_INVALID, "jfnk_residual: " + why);
   double nrm[3];
-  return eval_residual(u, nullptr, sref(1.0), nullptr, F, JS_F2_A, nrm);
+  return eval_residual(u, nullptr, sref(1.0), nullptr, F, nullptr, JS_F2_A, nrm);
 }
 
 int Engine::linearize(const double* x0, double rdiff) {
@@ -357,9 +360,9 @@ int Engine::linearize(const double* x0, double rdiff) {
   if (!(rdiff > 0)) rdiff = sqrt(kEps);
   ops_->copy(XT_, x0);
   double nrm[3];
-  int rc = eval_residual(XT_, nullptr, sref(1.0), nullptr, FX_, JS_F2_A, nrm);
+  int rc = eval_residual(XT_, nullptr, sref(1.0), nullptr, FX_, GX_, JS_F2_A, nrm);
   if (rc) return rc;
-  x0_ = XT_; f0_ = FX_;
+  x0_ = XT_; f0_ = FX_; g0_ = GX_;
   omega_ = rdiff * std::max(1.0, nrm[2]) / std::max(1.0, nrm[1]); // _nonlin.py:1552-1555
   if (cfg_.problem == JFNK_PROBLEM_SH) ops_->sh_bind_x0(x0_);
   return ops_->status();
@@ -376,7 +379,7 @@ void Engine::apply_operator(const double* z, int zn2_idx, double* w, bool unit_i
   ScalarRef sc = sref(omega_, -1, -1, zn2_idx);
   ScalarRef div = unit_input ? sref(omega_) : sc;
   if (cfg_.problem == JFNK_PROBLEM_SH) {
-    ops_->sh_jvp(x0_, z, sc, div, D_, f0_, w);
+    ops_->sh_jvp(x0_, z, sc, div, D_, f0_, g0_, w);
   } else if (cfg_.problem == JFNK_PROBLEM_PMA2) {
     ops_->pma2_eval(mp_, pp_, MF_, x0_, z, sc, UVAL_, CN_, f0_, div, scratch_.data(), nullptr, w, JS_TMP0 /*unused*/);
   } else {
@@ -603,15 +606,17 @@ int Engine::newton(double* u, const jfnk_newton_opts* o, jfnk_history* hist) {
   double* xt = XT_;
   double* Fx = FX_;
   double* Ft = FT_;
+  double* Gx = GX_; // (null for the mesh problems)
+  double* Gt = GT_;
   double nrm[3];
-  int rc = eval_residual(x, nullptr, sref(1.0), nullptr, Fx, JS_F2_A, nrm);
+  int rc = eval_residual(x, nullptr, sref(1.0), nullptr, Fx, Gx, JS_F2_A, nrm);
   if (rc) return rc;
   double f2 = nrm[0], fmax = nrm[1], xmax = nrm[2];
   double Fx_norm = sqrt(f2);
   if (hist) { hist->f0_max = fmax; hist->f0_l2 = Fx_norm; }
 
   ov_slots_.clear(); // KrylovJacobian is created per newton_krylov call: outer_v = [] (_nonlin.py:1508)
-  x0_ = x; f0_ = Fx;
+  x0_ = x; f0_ = Fx; g0_ = Gx;
   omega_ = rdiff * std::max(1.0, xmax) / std::max(1.0, fmax);
   if (cfg_.problem == JFNK_PROBLEM_SH) ops_->sh_bind_x0(x0_);
 
@@ -674,7 +679,7 @@ int Engine::newton(double* u, const jfnk_newton_opts* o, jfnk_history* hist) {
     double tn[3] = {0, 0, 0};
     double last_s = NAN;
     auto phi = [&](double sv, int& err) -> double {
-      err = eval_residual(x, sol, sref(-sv), xt, Ft, JS_F2_B, tn);
+      err = eval_residual(x, sol, sref(-sv), xt, Ft, Gt, JS_F2_B, tn);
       last_s = sv;
       if (!isfinite(tn[0])) return inf; // _safe_norm
       double nv = sqrt(tn[0]);
@@ -719,10 +724,11 @@ int Engine::newton(double* u, const jfnk_newton_opts* o, jfnk_history* hist) {
     // accept: x <- x + s dx, Fx <- F(x)
     std::swap(x, xt);
     std::swap(Fx, Ft);
+    std::swap(Gx, Gt);
     double Fx_norm_new = sqrt(tn[0]);
     f2 = tn[0]; fmax = tn[1]; xmax = tn[2];
     // jacobian.update(x, Fx)
-    x0_ = x; f0_ = Fx;
+    x0_ = x; f0_ = Fx; g0_ = Gx;
     omega_ = rdiff * std::max(1.0, xmax) / std::max(1.0, fmax);
     if (cfg_.problem == JFNK_PROBLEM_SH) ops_->sh_bind_x0(x0_);
     if (cb_) {
@@ -731,7 +737,7 @@ int Engine::newton(double* u, const jfnk_newton_opts* o, jfnk_history* hist) {
       if (stop_requested_) {
         stop_requested_ = false;
         if (x != u) ops_->copy(u, x);
-        x0_ = nullptr; f0_ = nullptr;
+        x0_ = nullptr; f0_ = nullptr; g0_ = nullptr;
         return fail(JFNK_INVALID, "newton_krylov: stopped by the callback");
       }
     }
@@ -754,7 +760,7 @@ int Engine::newton(double* u, const jfnk_newton_opts* o, jfnk_history* hist) {
     }
   }
   if (x != u) ops_->copy(u, x);
-  x0_ = nullptr; f0_ = nullptr; // the iterate buffers are about to be reused
+  x0_ = nullptr; f0_ = nullptr; g0_ = nullptr; // the iterate buffers are about to be reused
   if (hist) { hist->nfev = nfev_; hist->inner_iters = inner_total_; hist->reorth = reorth_total_; }
   int st = ops_->status();
   if (st) return st;

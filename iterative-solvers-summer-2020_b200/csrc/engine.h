@@ -71,7 +71,9 @@ class Engine {
  private:
   int fail(int code, const std::string& msg) { err_ = msg; return code; }
   // F(x + a v) with norms -> slot set norm_off; all-reduces the norms; host copy in nrm[3] = {sum F^2, max|F|, max|x|}
-  int eval_residual(const double* x, const double* v, ScalarRef a, double* xt_out, double* F, int norm_off, double nrm[3]);
+  // g_out (Swift-Hohenberg only, may be null): G = F + d of the evaluated point, see DeviceOps::sh_residual
+  int eval_residual(const double* x, const double* v, ScalarRef a, double* xt_out, double* F, double* g_out, int norm_off,
+                    double nrm[3]);
   // w = A (z * inv_norm) for the current linear operator
   // unit_input: z is treated as z/||z|| (Arnoldi vectors are stored unnormalised); else the SciPy matvec(v)
   void apply_operator(const double* z, int zn2_idx, double* w, bool unit_input);
@@ -95,6 +97,7 @@ class Engine {
   double* ws_;
   size_t vstride_;
   double *XT_, *FX_, *FT_, *D_;
+  double *GX_, *GT_; // Swift-Hohenberg: G(x) = F(x) + d of the iterate / the trial point (the FD quotient's subtrahend)
   std::vector<double*> scratch_; // scratch fields for the multi-kernel (mesh) residuals
   double* MF_[7];  // metric fields
   double *UVAL_, *CN_; // previous state and Crank-Nicolson term of the mesh problems
@@ -113,6 +116,7 @@ class Engine {
   // linearisation point of the Jacobian operator
   const double* x0_ = nullptr;
   const double* f0_ = nullptr;
+  const double* g0_ = nullptr; // G(x0) when the problem keeps it (Swift-Hohenberg), else null
   double omega_ = 0.0;
   bool linear_op_ = false; // true: SH_LINEAR operator instead of the FD Jacobian
 

@@ -40,7 +40,7 @@ struct ShBoxRows {
 
 template <int OP, bool HAS_V>
 struct BoxLayout {
-  static constexpr bool kHasD = (OP == OP_RESID || OP == OP_JVP || OP == OP_LINMV);
+  static constexpr bool kHasD = (OP == OP_RESID || OP == OP_JVP || OP == OP_JVPG || OP == OP_LINMV);
   static constexpr bool kHasF = (OP == OP_JVP || OP == OP_LINPREP);
   static constexpr int kFieldDoubles = kBoxMainDoubles + 2 * kBoxHaloDoubles; // main boxes, left halo, right halo
   static constexpr int kX = 0;
@@ -250,11 +250,12 @@ __global__ void __launch_bounds__(kBoxThreads, 2)
             double sdx = p0s.x + p2s.x, sdy = p0s.y + p2s.y;
             double s2x = q0s.x + u0.x + u4.x, s2y = q0s.y + u0.y + u4.y;
             const size_t e = (size_t)y * nx + xs + c0;
-            double2 o, o2 = zero2;
-            o.x = sh_value<OP>(P, scale, u2.x, s1x, sdx, s2x, dv.x, fv.x, o2.x, acc);
-            o.y = sh_value<OP>(P, scale, u2.y, s1y, sdy, s2y, dv.y, fv.y, o2.y, acc);
+            double2 o, o2 = zero2, o3 = zero2;
+            o.x = sh_value<OP>(P, scale, u2.x, s1x, sdx, s2x, dv.x, fv.x, o2.x, o3.x, acc);
+            o.y = sh_value<OP>(P, scale, u2.y, s1y, sdy, s2y, dv.y, fv.y, o2.y, o3.y, acc);
             stg2(A.out + e, o);
             if ((OP == OP_RESID && A.out2) || OP == OP_LINPREP) stg2(A.out2 + e, o2);
+            if (OP == OP_RESID && A.out3) stg2(A.out3 + e, o3);
           }
         }
         // this warp is done with the stage: hand it back to the producer

@@ -26,17 +26,20 @@
 
 namespace jfnk {
 
-enum ShOp { OP_LAP = 0, OP_L = 1, OP_SETPREV = 2, OP_RESID = 3, OP_JVP = 4, OP_LINPREP = 5, OP_LINMV = 6 };
+// OP_JVPG: the FD quotient against the stored G(x0) = F(x0) + d -- (G(x0 + sc z) - G(x0))/div, one pointwise operand
+// (32 B/point) instead of d and f0 (40 B/point); OP_JVP keeps the two-operand form for callers without G(x0).
+enum ShOp { OP_LAP = 0, OP_L = 1, OP_SETPREV = 2, OP_RESID = 3, OP_JVP = 4, OP_LINPREP = 5, OP_LINMV = 6, OP_JVPG = 7 };
 
 struct ShArgs {
   const double *x, *xtop, *xbot; // primary field and its 2-row halos (top = rows -2,-1; bot = rows nrows, nrows+1)
   const double *v, *vtop, *vbot; // optional second field: t = x + a v
   ScalarRef a;                   // combination coefficient
   ScalarRef div;                 // JVP divisor ; LINMV output scale
-  const double* d;               // RESID/JVP: per-step constant d ; LINMV: diagonal D
+  const double* d;               // RESID/JVP: per-step constant d ; LINMV: diagonal D ; JVPG: G(x0)
   const double* f0;              // JVP: f0 ; LINPREP: Uo
   double* out;                   // result field
   double* out2;                  // RESID: x + a v (may be null) ; LINPREP: D
+  double* out3;                  // RESID: G(x + a v) = F + d (may be null): what OP_JVPG subtracts once this point is accepted
   int nx, nrows;
   int norm_off;                  // RESID: S[norm_off..+2] = sum F^2, max|F|, max|t|
   // Fused halo exchange over peer memory (marching kernel, slab ranks): the kernel itself stores the first / last two rows of
@@ -60,14 +63,17 @@ struct ShAcc {
 // one output value (returned) plus the optional second output (RESID: x + a v ; LINPREP: D)
 template <int OP>
 __device__ __forceinline__ double sh_value(const SHParams& P, double scale, double uc, double s1, double sd, double s2,
-                                           double dval, double f0val, double& second, ShAcc& acc) {
+                                           double dval, double f0val, double& second, double& third, ShAcc& acc) {
   if (OP == OP_LAP) return sh_apply5(P, uc, s1);
   double Lu = sh_apply13(P, uc, s1, sd, s2);
   if (OP == OP_L) return Lu;
   if (OP == OP_SETPREV) return sh_prev_const(P, uc, Lu);
+  if (OP == OP_JVPG) return (sh_G(P, uc, Lu) - dval) * scale; // dval = G(x0), scale = 1/div
   if (OP == OP_RESID) {
-    double F = sh_G(P, uc, Lu) - dval;
+    double G = sh_G(P, uc, Lu);
+    double F = G - dval;
     second = uc;
+    third = G;
     acc.f2 = fma(F, F, acc.f2);
     acc.fmax = fmax(acc.fmax, fabs(F));
     acc.xmax = fmax(acc.xmax, fabs(uc));
@@ -86,7 +92,7 @@ __device__ __forceinline__ double sh_value(const SHParams& P, double scale, doub
 
 template <int OP>
 __device__ __forceinline__ double sh_scale(const ShArgs& A, const double* S) {
-  if (OP == OP_JVP) return 1.0 / eval_sref(S, A.div);
+  if (OP == OP_JVP || OP == OP_JVPG) return 1.0 / eval_sref(S, A.div);
   if (OP == OP_LINMV) return eval_sref(S, A.div);
   return 1.0;
 }
@@ -119,11 +125,12 @@ __global__ void __launch_bounds__(256) sh_point_kernel(ShArgs A, SHParams P, dou
     double s1 = a1 + at(r - 1, c) + at(r + 1, c);
     double sd = a1u + a1d;
     double s2 = a2 + at(r - 2, c) + at(r + 2, c);
-    double dval = (OP == OP_RESID || OP == OP_JVP || OP == OP_LINMV) ? A.d[e] : 0.0;
+    double dval = (OP == OP_RESID || OP == OP_JVP || OP == OP_JVPG || OP == OP_LINMV) ? A.d[e] : 0.0;
     double f0val = (OP == OP_JVP || OP == OP_LINPREP) ? A.f0[e] : 0.0;
-    double second = 0.0;
-    A.out[e] = sh_value<OP>(P, scale, uc, s1, sd, s2, dval, f0val, second, acc);
+    double second = 0.0, third = 0.0;
+    A.out[e] = sh_value<OP>(P, scale, uc, s1, sd, s2, dval, f0val, second, third, acc);
     if ((OP == OP_RESID && A.out2) || OP == OP_LINPREP) A.out2[e] = second;
+    if (OP == OP_RESID && A.out3) A.out3[e] = third;
   }
   if (OP == OP_RESID) {
     double val[3] = {acc.f2, acc.fmax, acc.xmax};
@@ -170,7 +177,7 @@ __device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t by
 
 template <int OP, bool HAS_V>
 struct TmaLayout {
-  static constexpr bool kHasD = (OP == OP_RESID || OP == OP_JVP || OP == OP_LINMV);
+  static constexpr bool kHasD = (OP == OP_RESID || OP == OP_JVP || OP == OP_JVPG || OP == OP_LINMV);
   static constexpr bool kHasF = (OP == OP_JVP || OP == OP_LINPREP);
   static constexpr int kX = 0;                                  // offsets in doubles inside one stage
   static constexpr int kV = kTmaTX + 4;
@@ -343,11 +350,12 @@ __global__ void __launch_bounds__(kTmaThreads) sh_tma_kernel(ShArgs A, SHParams 
           double sdx = p0.x + p2.x, sdy = p0.y + p2.y;
           double s2x = q0.x + u0.x + u4.x, s2y = q0.y + u0.y + u4.y;
           const size_t e = (size_t)y * nx + xs + t2;
-          double2 o, o2 = zero2;
-          o.x = sh_value<OP>(P, scale, u2.x, s1x, sdx, s2x, dv.x, fv.x, o2.x, acc);
-          o.y = sh_value<OP>(P, scale, u2.y, s1y, sdy, s2y, dv.y, fv.y, o2.y, acc);
+          double2 o, o2 = zero2, o3 = zero2;
+          o.x = sh_value<OP>(P, scale, u2.x, s1x, sdx, s2x, dv.x, fv.x, o2.x, o3.x, acc);
+          o.y = sh_value<OP>(P, scale, u2.y, s1y, sdy, s2y, dv.y, fv.y, o2.y, o3.y, acc);
           stg2(A.out + e, o);
           if ((OP == OP_RESID && A.out2) || OP == OP_LINPREP) stg2(A.out2 + e, o2);
+          if (OP == OP_RESID && A.out3) stg2(A.out3 + e, o3);
         }
       }
       idx = run_end;

@@ -188,7 +188,7 @@ class HostOps : public DeviceOps {
       }
   }
   void sh_residual(const double* x, const double* v, ScalarRef a, const double* d, double* xt_out, double* F,
-                   int norm_off) override {
+                   double* g_out, int norm_off) override {
     launches_++;
     std::vector<double> t, top, bot;
     combined(x, v, eval_sref(S_.data(), a), t, top, bot);
@@ -199,8 +199,10 @@ class HostOps : public DeviceOps {
         double uc, s1, sd, s2;
         sums(f, r, c, uc, s1, sd, s2);
         size_t e = (size_t)r * g_.nx + c;
-        double Fv = sh_G(shp_, uc, sh_apply13(shp_, uc, s1, sd, s2)) - d[e];
+        double Gv = sh_G(shp_, uc, sh_apply13(shp_, uc, s1, sd, s2));
+        double Fv = Gv - d[e];
         F[e] = Fv;
+        if (g_out) g_out[e] = Gv;
         f2 += Fv * Fv; fm = fmax(fm, fabs(Fv)); xm = fmax(xm, fabs(uc));
         if (!(fabs(Fv) <= 1.79e308)) fm = INFINITY; // NaN/inf poison like np.abs(F).max()
       }
@@ -209,7 +211,7 @@ class HostOps : public DeviceOps {
   }
   void sh_bind_x0(const double*) override {}
   void sh_jvp(const double* x0, const double* z, ScalarRef sc, ScalarRef div, const double* d, const double* f0,
-              double* w) override {
+              const double* g0, double* w) override {
     launches_++;
     std::vector<double> t, top, bot;
     combined(x0, z, eval_sref(S_.data(), sc), t, top, bot);
@@ -220,8 +222,8 @@ class HostOps : public DeviceOps {
         double uc, s1, sd, s2;
         sums(f, r, c, uc, s1, sd, s2);
         size_t e = (size_t)r * g_.nx + c;
-        double Fv = sh_G(shp_, uc, sh_apply13(shp_, uc, s1, sd, s2)) - d[e];
-        w[e] = (Fv - f0[e]) / dv;
+        double Gv = sh_G(shp_, uc, sh_apply13(shp_, uc, s1, sd, s2));
+        w[e] = g0 ? (Gv - g0[e]) * (1.0 / dv) : ((Gv - d[e]) - f0[e]) / dv;
       }
   }
   void shlin_prepare(const double* U, const double* Uo, double* D, double* b) override {

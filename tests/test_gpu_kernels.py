@@ -18,10 +18,12 @@ def rel(a, b):
     return np.linalg.norm(np.ravel(a) - np.ravel(b)) / np.linalg.norm(np.ravel(b))
 
 
-@pytest.mark.parametrize("N", [64, 130, 256, 520])
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("N", [64, 130, 256, 520, 1030])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_stencil_kernels_both_variants_vs_oracle(cuda_buffers, N, variant):
-    """variant 2 forces the marching kernel (even N), variant 1 the per-point kernel."""
+    """variant 1: the per-point kernel; 2: the marching kernel with 1-D bulk-copy staging (even N); 3: the marching kernel
+    with tensor-map TMA boxes (even N >= 256; 520 and 1030 have a partial last strip that the TMA unit zero-fills, 256 a
+    single-box strip; below 256 variant 3 is the per-point kernel)."""
     h = 0.625
     o = SHOracle(N=N, d=h * N)
     F = jf.SHResidual(N=N, d=h * N, buffers=cuda_buffers, kernel_variant=variant)
@@ -49,12 +51,31 @@ def test_marching_and_point_kernels_agree_bitwise(cuda_buffers):
     N = 256
     u = seeded_state(N, 0)
     outs = []
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         F = jf.SHResidual(N=N, d=0.625 * N, buffers=cuda_buffers, kernel_variant=variant)
         F.set_prev(u)
         outs.append((F.spmv_L(u), F.spmv_lap(u), F(u + 0.5)))
-    for a, b in zip(*outs):
-        assert np.array_equal(a, b)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("N", [512, 776])
+def test_box_kernel_solver_paths(cuda_buffers, N):
+    """every operation of the tensor-map marching kernel inside the solvers: implicit steps (set_prev, residual with and
+    without the line-search operand, FD-JVP) and the linearised stepper (prepare + matvec), against the per-point kernel."""
+    h = 0.625
+    U0 = seeded_state(N)
+    res = {}
+    for variant in (1, 3):
+        F = jf.SHResidual(N=N, d=h * N, buffers=cuda_buffers, kernel_variant=variant)
+        hist = []
+        U = F.steps(U0, 2, history=hist)
+        S = jf.SHLinearised(N=N, d=h * N, buffers=cuda_buffers, kernel_variant=variant)
+        V, _ = S.steps(0.1 * U0, nsteps=2)
+        res[variant] = (U, [h_["nit"] for h_ in hist], V)
+    assert rel(res[3][0], res[1][0]) < 1e-9 and res[3][1] == res[1][1]
+    assert rel(res[3][2], res[1][2]) < 1e-11
 
 
 @pytest.mark.parametrize("ny,nx,nv", [(8, 512, 0), (7, 585, 1), (5, 2001, 3), (16, 4096, 8), (7, 9363, 9),
