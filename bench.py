@@ -389,12 +389,12 @@ def main():
         v = prof[dom]
         ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")
         if os.path.exists(tpath):
             rec = json.load(open(tpath)).get(dom)
             if rec:  # DRAM bytes per launch = algorithmic bytes per launch x (ncu DRAM bytes / algorithmic bytes of the captured launch)
                 traffic = v["bytes"] / v["launches"] * rec["dram_bytes"] / rec["algorithmic_bytes"]
-                traffic_src = f"ncu --set full on {rec['kernel']}: dram read+write = {rec['dram_bytes'] / rec['algorithmic_bytes']:.3f} x algorithmic (profiles/ncu_traffic_r1.json)"
+                traffic_src = f"ncu --set full on {rec['kernel']}: dram read+write = {rec['dram_bytes'] / rec['algorithmic_bytes']:.3f} x algorithmic (profiles/ncu_traffic_r2.json)"
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "bytes_per_launch": v["bytes"] / v["launches"], "ms_per_launch": v["ms"] / v["launches"],

@@ -5,6 +5,7 @@
 //   mdot   (nv vectors) : (nv + 1) * 8 B          gs_update / maxpy_sub : (nv + 2) * 8 B      maxpy : (nz + 1) * 8 B
 #pragma once
 #include "cuda_common.cuh"
+#include "p2p_kernels.cuh"
 
 namespace jfnk {
 
@@ -14,7 +15,8 @@ namespace jfnk {
 // (two 256-thread CTAs per SM: <= 128 registers, checked with -Xptxas -v; one CTA/SM starves the memory pipe)
 template <int NV, int U>
 __global__ void __launch_bounds__(256, 2) mdot_kernel(PtrList V, int nv, const double* __restrict__ w, size_t n,
-                                                      double* S, int out_off, ReduceWs ws) {
+                                                      double* S, int out_off, ReduceWs ws, P2PReduceArgs R) {
+  if (S[JS_STOP] != 0.0) return; // speculatively enqueued Arnoldi step after the process stopped
   double acc[NV + 1];
 #pragma unroll
   for (int k = 0; k <= NV; ++k) acc[k] = 0.0;
@@ -56,13 +58,16 @@ __global__ void __launch_bounds__(256, 2) mdot_kernel(PtrList V, int nv, const d
     acc[NV] = fma(we, we, acc[NV]);
   }
   // acc[0..nv) are the dots, acc[NV] is w.w; the reduction writes them contiguously: out[0..nv-1], out[nv]
-  grid_reduce_sums<NV + 1>(acc, nv, ws, S + out_off);
+  const bool last = grid_reduce_sums<NV + 1>(acc, nv, ws, S + out_off);
+  // slab ranks: the finalising CTA all-reduces the nv + 1 sums over peer memory (no separate collective launch)
+  if (last && R.nranks > 1) p2p_allreduce_block(R);
 }
 
 // scalar-load variant for vectors that are not 16-byte aligned / odd leading dimension
 template <int NV>
 __global__ void __launch_bounds__(256) mdot_scalar_kernel(PtrList V, int nv, const double* __restrict__ w, size_t n,
-                                                          double* S, int out_off, ReduceWs ws) {
+                                                          double* S, int out_off, ReduceWs ws, P2PReduceArgs R) {
+  if (S[JS_STOP] != 0.0) return;
   double acc[NV + 1];
 #pragma unroll
   for (int k = 0; k <= NV; ++k) acc[k] = 0.0;
@@ -74,7 +79,8 @@ __global__ void __launch_bounds__(256) mdot_scalar_kernel(PtrList V, int nv, con
       if (k < nv) acc[k] = fma(V.p[k][i], wv, acc[k]);
     acc[NV] = fma(wv, wv, acc[NV]);
   }
-  grid_reduce_sums<NV + 1>(acc, nv, ws, S + out_off);
+  const bool last = grid_reduce_sums<NV + 1>(acc, nv, ws, S + out_off);
+  if (last && R.nranks > 1) p2p_allreduce_block(R);
 }
 
 // MODE 0: w -= sum_i (S[c_off+i]/S[JS_VN2+i]) V_i   (Gram-Schmidt update with unnormalised basis vectors)
@@ -86,7 +92,8 @@ __global__ void __launch_bounds__(256) mdot_scalar_kernel(PtrList V, int nv, con
 // issued back to back), U = double2 elements per thread per sweep.
 template <int MODE, int NV, int U>
 __global__ void __launch_bounds__(256, 2) maxpy_kernel(PtrList V, int nv, double* __restrict__ w, size_t n, double* S,
-                                                       int c_off, int n2_off, int fuse_j, ReduceWs ws) {
+                                                       int c_off, int n2_off, int fuse_j, ReduceWs ws, P2PReduceArgs R) {
+  if (S[JS_STOP] != 0.0) return; // (the host clears JS_STOP before it assembles dx with MODE 2)
   __shared__ double c[JF_MAXV];
   if (threadIdx.x < JF_MAXV) {
     double cv = 0.0;
@@ -149,14 +156,20 @@ __global__ void __launch_bounds__(256, 2) maxpy_kernel(PtrList V, int nv, double
     acc[0] = fma(tt, tt, acc[0]);
   }
   const bool last = grid_reduce<1>(acc, 0u, ws, S + n2_off);
-  // single-GPU fusion: the finalising CTA's thread 0 (which just wrote the norm) does the Givens step of column j
-  if (MODE == 0 && fuse_j >= 0 && last && threadIdx.x == 0) hess_givens_step(S, fuse_j, 0, 0);
+  // The finalising CTA goes on: with slab ranks it all-reduces the norm over peer memory and then (R.givens_j >= 0) runs
+  // the Givens step of the column on the reduced value; on one GPU its thread 0 (which just wrote the norm) runs the
+  // Givens step of column fuse_j directly.  Either way an Arnoldi step is operator + multi-dot + this kernel.
+  if (last) {
+    if (R.nranks > 1) p2p_allreduce_block(R);
+    else if (MODE == 0 && fuse_j >= 0 && threadIdx.x == 0) hess_givens_step(S, fuse_j, R.givens_taken, R.givens_rerun);
+  }
 }
 
 // scalar-load variant for operands that are not 16-byte aligned
 template <int MODE>
 __global__ void __launch_bounds__(256) maxpy_scalar_kernel(PtrList V, int nv, double* __restrict__ w, size_t n, double* S,
-                                                           int c_off, int n2_off, int fuse_j, ReduceWs ws) {
+                                                           int c_off, int n2_off, int fuse_j, ReduceWs ws, P2PReduceArgs R) {
+  if (S[JS_STOP] != 0.0) return;
   __shared__ double c[JF_MAXV];
   __shared__ const double* vp[JF_MAXV];
   if (threadIdx.x < nv) {
@@ -175,7 +188,10 @@ __global__ void __launch_bounds__(256) maxpy_scalar_kernel(PtrList V, int nv, do
     acc[0] = fma(t, t, acc[0]);
   }
   const bool last = grid_reduce<1>(acc, 0u, ws, S + n2_off);
-  if (MODE == 0 && fuse_j >= 0 && last && threadIdx.x == 0) hess_givens_step(S, fuse_j, 0, 0);
+  if (last) {
+    if (R.nranks > 1) p2p_allreduce_block(R);
+    else if (MODE == 0 && fuse_j >= 0 && threadIdx.x == 0) hess_givens_step(S, fuse_j, R.givens_taken, R.givens_rerun);
+  }
 }
 
 // out = a x + b y (y may be null), optional ||out||^2
@@ -226,7 +242,10 @@ __global__ void __launch_bounds__(256) maxabs_kernel(const double* v, size_t n, 
   grid_reduce<1>(acc, 1u, ws, S + out_off);
 }
 
-__global__ void givens_kernel(double* S, int j, int taken, int rerun) { hess_givens_step(S, j, taken, rerun); }
+__global__ void givens_kernel(double* S, int j, int taken, int rerun, int skippable) {
+  if (skippable && S[JS_STOP] != 0.0) return;
+  hess_givens_step(S, j, taken, rerun);
+}
 
 struct IdxList {
   int v[JF_MAXV];

@@ -27,6 +27,10 @@ __device__ __forceinline__ double2 ldg2(const double* p) {
 }
 __device__ __forceinline__ double ldg1(const double* p) { return __ldg(p); }
 __device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+// streaming store: the line is written once and not read again by this kernel (evict-first in L2)
+__device__ __forceinline__ void stg2_cs(double* p, double2 v) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
 
 // x + a*v exactly as NumPy evaluates `x0 + sc*v` (product rounded, then sum rounded; never contracted to an FMA)
 __device__ __forceinline__ double combine(double x, double a, double v) { return __dadd_rn(x, __dmul_rn(a, v)); }
@@ -92,7 +96,7 @@ __device__ __forceinline__ bool grid_reduce(double (&val)[K], unsigned maxmask, 
 // multi-dot variant: val[0..nv) are dot accumulators (nv <= KMAX-1 at run time), val[KMAX-1] is w.w.
 // Writes out[0..nv) = dots, out[nv] = w.w.  All array indices are compile-time so val[] stays in registers.
 template <int KMAX>
-__device__ __forceinline__ void grid_reduce_sums(double (&val)[KMAX], int nv, const ReduceWs& ws, double* out) {
+__device__ __forceinline__ bool grid_reduce_sums(double (&val)[KMAX], int nv, const ReduceWs& ws, double* out) {
   __shared__ double sm[8][KMAX];
   __shared__ bool is_last;
   const int K = nv + 1;
@@ -131,6 +135,7 @@ __device__ __forceinline__ void grid_reduce_sums(double (&val)[KMAX], int nv, co
     }
     if (threadIdx.x == 0) *ws.ticket = 0u;
   }
+  return is_last; // true in every thread of the CTA that finalised
 }
 
 } // namespace jfnk

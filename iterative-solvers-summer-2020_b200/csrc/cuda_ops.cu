@@ -51,6 +51,9 @@ class CudaOps : public DeviceOps {
     if (!ck(cudaMalloc(&ws_.ticket, sizeof(unsigned)), "cudaMalloc(ticket)")) { why = err_; return; }
     if (!ck(cudaMemsetAsync(ws_.ticket, 0, sizeof(unsigned), stream_), "cudaMemset(ticket)")) { why = err_; return; }
     if (!ck(cudaMallocHost(&pinned_, sizeof(double) * (JS_COUNT + 1)), "cudaMallocHost")) { why = err_; return; }
+    if (!ck(cudaMallocHost(&posted_pin_, sizeof(double) * (JF_MAXV + 2) * 8), "cudaMallocHost")) { why = err_; return; }
+    for (int i = 0; i < JF_MAXV + 2; ++i)
+      if (!ck(cudaEventCreateWithFlags(&posted_ev_[i], cudaEventDisableTiming), "cudaEventCreate")) { why = err_; return; }
     if (g_.nranks > 1) {
       // row halos of the linearisation point (x0), of the operand vector (z / dx) and of a generic field; the top and the
       // bottom pair of a slot are adjacent (4 rows) so that one tensor map describes both (sh_box_kernel)
@@ -83,6 +86,8 @@ class CudaOps : public DeviceOps {
     if (dctx_) cudaFree(dctx_);
     if (dcty_) cudaFree(dcty_);
     if (pinned_) cudaFreeHost(pinned_);
+    if (posted_pin_) cudaFreeHost(posted_pin_);
+    for (int i = 0; i < JF_MAXV + 2; ++i) if (posted_ev_[i]) cudaEventDestroy(posted_ev_[i]);
     if (ws_.ticket) cudaFree(ws_.ticket);
     if (ws_.partials) cudaFree(ws_.partials);
     if (S_) cudaFree(S_);
@@ -189,6 +194,19 @@ class CudaOps : public DeviceOps {
       err_ = "peer-memory collective timed out: a rank did not reach the matching halo exchange / all-reduce";
     }
   }
+  // Without peer memory the collectives are NCCL calls, which cannot be dropped on the device: no speculation there.
+  bool can_speculate() const override {
+    const char* e = getenv("JFNK_SPECULATE"); // (read per cycle: the parity tests flip it)
+    return !(e && atoi(e) == 0) && (g_.nranks == 1 || p2p_);
+  }
+  void post_read(int slot, int off, int cnt) override {
+    if (!ck(cudaMemcpyAsync(posted_pin_ + 8 * slot, S_ + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, stream_), "D2H record")) return;
+    ck(cudaEventRecord(posted_ev_[slot], stream_), "cudaEventRecord");
+  }
+  void wait_read(int slot, int cnt, double* host) override {
+    if (!ck(cudaEventSynchronize(posted_ev_[slot]), "cudaEventSynchronize")) return;
+    memcpy(host, posted_pin_ + 8 * slot, sizeof(double) * cnt);
+  }
   void write_scalars(int off, int cnt, const double* host) override {
     ck(cudaMemcpyAsync(S_ + off, host, sizeof(double) * cnt, cudaMemcpyHostToDevice, stream_), "H2D scalars");
   }
@@ -203,7 +221,7 @@ class CudaOps : public DeviceOps {
     nck(nccl_->AllReduce(S_ + off, S_ + off, cnt, ncclDouble, ncclMax, comm_, stream_), "ncclAllReduce(max)");
   }
   void allreduce_sum_givens(int off, int cnt, int j, int taken, int rerun) override {
-    if (g_.nranks > 1 && p2p_ && cnt <= kP2PMaxScalars) { p2p_allreduce(off, cnt, 0, j, taken, rerun); return; }
+    if (g_.nranks > 1 && p2p_ && cnt <= kP2PMaxScalars) { p2p_allreduce(off, cnt, 0, j, taken, rerun, 1); return; }
     allreduce_sum(off, cnt);
     givens(j, taken, rerun);
   }
@@ -233,42 +251,52 @@ class CudaOps : public DeviceOps {
   }
 
   template <int NV>
-  void mdot_launch(bool vec, const PtrList& L, int nv, const double* w, int out_off) {
+  void mdot_launch(bool vec, const PtrList& L, int nv, const double* w, int out_off, const P2PReduceArgs& R) {
     size_t n = g_.n();
     constexpr int U = NV <= 4 ? 4 : (NV <= 8 ? 2 : 1);
     Prof prof(this, out_off == JS_RD2 ? K_MDOT2 : K_MDOT, nb(nv + 1));
-    if (vec) mdot_kernel<NV, U><<<resident_grid(mdot_kernel<NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, ws_);
-    else mdot_scalar_kernel<NV><<<resident_grid(mdot_scalar_kernel<NV>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, ws_);
+    if (vec) mdot_kernel<NV, U><<<resident_grid(mdot_kernel<NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, ws_, R);
+    else mdot_scalar_kernel<NV><<<resident_grid(mdot_scalar_kernel<NV>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, ws_, R);
   }
-  void mdot(int nv, const double* const* V, const double* w, int out_off) override {
+  void mdot(int nv, const double* const* V, const double* w, int out_off) override { mdot_any(nv, V, w, out_off, false); }
+  // local sums + all-reduce over the slab ranks; with peer memory the finalising CTA of the kernel does the exchange
+  void mdot_reduced(int nv, const double* const* V, const double* w, int out_off) override {
+    if (g_.nranks == 1) { mdot_any(nv, V, w, out_off, false); return; }
+    if (fused_reduce(nv + 1)) { mdot_any(nv, V, w, out_off, true); return; }
+    mdot_any(nv, V, w, out_off, false);
+    allreduce_sum(out_off, nv + 1);
+  }
+  void mdot_any(int nv, const double* const* V, const double* w, int out_off, bool reduce) {
     if (nv > 32) {
       // more than 32 accumulators per thread would drop to one CTA per SM: two passes of <= 24 vectors instead
       // (w is read twice: +1 of nv+1 vectors).  The first pass parks w.w at out[h]; the second overwrites it.
       int h = nv / 2;
-      mdot(h, V, w, out_off);
-      mdot_part(nv - h, V + h, w, out_off + h);
+      mdot_part(h, V, w, out_off, reduce);
+      mdot_part(nv - h, V + h, w, out_off + h, reduce);
       return;
     }
-    mdot_part(nv, V, w, out_off);
+    mdot_part(nv, V, w, out_off, reduce);
   }
-  void mdot_part(int nv, const double* const* V, const double* w, int out_off) {
+  void mdot_part(int nv, const double* const* V, const double* w, int out_off, bool reduce) {
     PtrList L;
     bool vec = aligned16(w);
     for (int i = 0; i < nv; ++i) { L.p[i] = V[i]; vec = vec && aligned16(V[i]); }
     for (int i = nv; i < JF_MAXV; ++i) L.p[i] = nullptr;
-    if (nv <= 2) mdot_launch<2>(vec, L, nv, w, out_off);
-    else if (nv <= 4) mdot_launch<4>(vec, L, nv, w, out_off);
-    else if (nv <= 8) mdot_launch<8>(vec, L, nv, w, out_off);
-    else if (nv <= 12) mdot_launch<12>(vec, L, nv, w, out_off);
-    else if (nv <= 16) mdot_launch<16>(vec, L, nv, w, out_off);
-    else if (nv <= 20) mdot_launch<20>(vec, L, nv, w, out_off);
-    else if (nv <= 24) mdot_launch<24>(vec, L, nv, w, out_off);
-    else if (nv <= 28) mdot_launch<28>(vec, L, nv, w, out_off);
-    else mdot_launch<32>(vec, L, nv, w, out_off);
+    const P2PReduceArgs R = reduce ? p2p_next_reduce(out_off, nv + 1, 0, -1, 0, 0, 1) : no_reduce();
+    if (nv <= 2) mdot_launch<2>(vec, L, nv, w, out_off, R);
+    else if (nv <= 4) mdot_launch<4>(vec, L, nv, w, out_off, R);
+    else if (nv <= 8) mdot_launch<8>(vec, L, nv, w, out_off, R);
+    else if (nv <= 12) mdot_launch<12>(vec, L, nv, w, out_off, R);
+    else if (nv <= 16) mdot_launch<16>(vec, L, nv, w, out_off, R);
+    else if (nv <= 20) mdot_launch<20>(vec, L, nv, w, out_off, R);
+    else if (nv <= 24) mdot_launch<24>(vec, L, nv, w, out_off, R);
+    else if (nv <= 28) mdot_launch<28>(vec, L, nv, w, out_off, R);
+    else mdot_launch<32>(vec, L, nv, w, out_off, R);
   }
 
   template <int MODE>
-  void maxpy_launch(int nv, const double* const* V, double* w, int c_off, int n2_off, int fuse_j) {
+  void maxpy_launch(int nv, const double* const* V, double* w, int c_off, int n2_off, int fuse_j,
+                    const P2PReduceArgs& R = no_reduce()) {
     PtrList L;
     bool vec = aligned16(w);
     for (int i = 0; i < nv; ++i) { L.p[i] = V[i]; vec = vec && aligned16(V[i]); }
@@ -276,22 +304,31 @@ class CudaOps : public DeviceOps {
     size_t n = g_.n();
     Prof prof(this, MODE == 2 ? K_MAXPY : (c_off == JS_RD2 ? K_GS_UPDATE2 : K_GS_UPDATE), nb(MODE == 2 ? nv + 1 : nv + 2));
     if (!vec) {
-      maxpy_scalar_kernel<MODE><<<resident_grid(maxpy_scalar_kernel<MODE>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, fuse_j, ws_);
-    } else if (nv <= 4) maxpy_vec<MODE, 4, 4>(L, nv, w, c_off, n2_off, fuse_j);
-    else if (nv <= 8) maxpy_vec<MODE, 8, 2>(L, nv, w, c_off, n2_off, fuse_j);
-    else if (nv <= 16) maxpy_vec<MODE, 16, 1>(L, nv, w, c_off, n2_off, fuse_j);
-    else if (nv <= 24) maxpy_vec<MODE, 24, 1>(L, nv, w, c_off, n2_off, fuse_j);
-    else if (nv <= 32) maxpy_vec<MODE, 32, 1>(L, nv, w, c_off, n2_off, fuse_j);
-    else maxpy_vec<MODE, JF_MAXV, 1>(L, nv, w, c_off, n2_off, fuse_j);
+      maxpy_scalar_kernel<MODE><<<resident_grid(maxpy_scalar_kernel<MODE>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, fuse_j, ws_, R);
+    } else if (nv <= 4) maxpy_vec<MODE, 4, 4>(L, nv, w, c_off, n2_off, fuse_j, R);
+    else if (nv <= 8) maxpy_vec<MODE, 8, 2>(L, nv, w, c_off, n2_off, fuse_j, R);
+    else if (nv <= 16) maxpy_vec<MODE, 16, 1>(L, nv, w, c_off, n2_off, fuse_j, R);
+    else if (nv <= 24) maxpy_vec<MODE, 24, 1>(L, nv, w, c_off, n2_off, fuse_j, R);
+    else if (nv <= 32) maxpy_vec<MODE, 32, 1>(L, nv, w, c_off, n2_off, fuse_j, R);
+    else maxpy_vec<MODE, JF_MAXV, 1>(L, nv, w, c_off, n2_off, fuse_j, R);
   }
   // few vectors -> several elements per thread, so that every thread keeps >= 8 independent loads in flight
   template <int MODE, int NV, int U>
-  void maxpy_vec(const PtrList& L, int nv, double* w, int c_off, int n2_off, int fuse_j) {
+  void maxpy_vec(const PtrList& L, int nv, double* w, int c_off, int n2_off, int fuse_j, const P2PReduceArgs& R) {
     size_t n = g_.n();
-    maxpy_kernel<MODE, NV, U><<<resident_grid(maxpy_kernel<MODE, NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, fuse_j, ws_);
+    maxpy_kernel<MODE, NV, U><<<resident_grid(maxpy_kernel<MODE, NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, fuse_j, ws_, R);
   }
   void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int fuse_givens_j) override {
     maxpy_launch<0>(nv, V, w, rd_off, n2_off, g_.nranks == 1 ? fuse_givens_j : -1);
+  }
+  // update + (all-reduced) norm + Givens step of column j in ONE launch: on one GPU the finalising CTA's thread 0 runs
+  // the Givens step; with peer memory the finalising CTA first all-reduces the norm with the other ranks
+  void gs_update_givens(int nv, const double* const* V, double* w, int rd_off, int n2_off, int j, int taken,
+                        int rerun) override {
+    if (g_.nranks == 1) { maxpy_launch<0>(nv, V, w, rd_off, n2_off, j, no_reduce(taken, rerun)); return; }
+    if (fused_reduce(1)) { maxpy_launch<0>(nv, V, w, rd_off, n2_off, -1, p2p_next_reduce(n2_off, 1, 0, j, taken, rerun, 1)); return; }
+    maxpy_launch<0>(nv, V, w, rd_off, n2_off, -1);
+    allreduce_sum_givens(n2_off, 1, j, taken, rerun);
   }
   void maxpy_sub(int nv, const double* const* V, double* w, int n2_off) override {
     maxpy_launch<1>(nv, V, w, JS_COEF, n2_off, -1);
@@ -323,7 +360,7 @@ class CudaOps : public DeviceOps {
   }
   void givens(int j, int taken, int rerun) override {
     Prof prof(this, K_SCALAR, 0.0);
-    givens_kernel<<<1, 1, 0, stream_>>>(S_, j, taken, rerun);
+    givens_kernel<<<1, 1, 0, stream_>>>(S_, j, taken, rerun, 1);
   }
   void lsq(int nit, const int* zn2_idx, int scale_n2_idx) override {
     IdxList L;
@@ -487,10 +524,20 @@ class CudaOps : public DeviceOps {
       ctas_per_sm = nb_ > 0 ? nb_ : 1;
     }
     // persistent grid: every CTA resident, each owning an equal contiguous range of (strip, row pair) units (>= 8 pairs)
-    long long total = (long long)((g_.nx + kBoxStrip - 1) / kBoxStrip) * (g_.nrows / kBoxR);
+    const long long strips = (g_.nx + kBoxStrip - 1) / kBoxStrip;
+    long long total = strips * (g_.nrows / kBoxR);
     long long blocks = std::min<long long>((long long)sms_ * ctas_per_sm, std::max<long long>(1, total / 8));
     if (blocks > kMaxBlocks) blocks = kMaxBlocks;
-    sh_box_kernel<OP, HAS_V><<<(int)blocks, kBoxThreads, LY::kSmemBytes, stream_>>>(M, A, hr, shp_, S_, ws_);
+    // measured at 16384^2 (profiles/spmv_box_modes_r2.log): streaming stores + band-major mapping 0.907 / 0.889 of the copy peak
+    // (Lap / L) against 0.889 / 0.860 without either
+    static const int mode_env = getenv("JFNK_BOX_MODE") ? atoi(getenv("JFNK_BOX_MODE")) : 3;
+    ShArgs B = A;
+    B.mode = mode_env & 1;
+    if ((mode_env & 2) && blocks >= strips && (g_.nrows / kBoxR) / (blocks / strips) >= 8) {
+      B.mode |= 2;
+      blocks = strips * (blocks / strips);
+    }
+    sh_box_kernel<OP, HAS_V><<<(int)blocks, kBoxThreads, LY::kSmemBytes, stream_>>>(M, B, hr, shp_, S_, ws_);
     return true;
   }
 
@@ -858,7 +905,7 @@ class CudaOps : public DeviceOps {
   // [parity][rank][64], arrival flags and an error word; every rank maps every peer's block.
   size_t p2p_halo_doubles() const { return 2 * (size_t)g_.nx; }
   size_t p2p_off_mail() const { return sizeof(double) * p2p_halo_doubles() * kP2PHaloSlots * 2 * 2; }
-  size_t p2p_off_flags() const { return p2p_off_mail() + sizeof(double) * 2 * kP2PMaxRanks * kP2PMaxScalars; }
+  size_t p2p_off_flags() const { return p2p_off_mail() + sizeof(double) * 4 * kP2PMaxRanks * kP2PMaxScalars; }
   size_t p2p_off_err() const { return p2p_off_flags() + sizeof(unsigned long long) * (kP2PHaloSlots * 2 + kP2PMaxRanks); }
   size_t p2p_bytes() const { return p2p_off_err() + 64; }
   unsigned* p2p_ticket() const { return reinterpret_cast<unsigned*>(peer_[g_.rank] + p2p_off_err() + 16); }
@@ -876,9 +923,11 @@ class CudaOps : public DeviceOps {
   }
   int* p2p_err() const { return reinterpret_cast<int*>(peer_[g_.rank] + p2p_off_err()); }
 
-  void p2p_allreduce(int off, int cnt, int op, int givens_j, int taken, int rerun) {
+  // arguments of the next peer-memory all-reduce (allocates its epoch): run by p2p_allreduce_kernel or, fused, by the
+  // finalising CTA of a multi-dot / update kernel
+  P2PReduceArgs p2p_next_reduce(int off, int cnt, int op, int givens_j, int taken, int rerun, int skippable) {
     const unsigned long long e = ++reduce_epoch_;
-    const int par = (int)(e & 1ull);
+    const int par = (int)(e & 3ull);
     P2PReduceArgs A;
     memset(&A, 0, sizeof(A));
     A.S = S_; A.off = off; A.cnt = cnt; A.op = op; A.rank = g_.rank; A.nranks = g_.nranks;
@@ -887,7 +936,23 @@ class CudaOps : public DeviceOps {
     A.my_flags = p2p_rflags(g_.rank);
     A.epoch = e;
     A.givens_j = givens_j; A.givens_taken = taken; A.givens_rerun = rerun;
+    A.skippable = skippable;
     A.err = p2p_err();
+    return A;
+  }
+  // "no collective": what the BLAS kernels get on one rank / without peer memory
+  static P2PReduceArgs no_reduce(int taken = 0, int rerun = 0) {
+    P2PReduceArgs A;
+    memset(&A, 0, sizeof(A));
+    A.nranks = 1; A.givens_j = -1; A.givens_taken = taken; A.givens_rerun = rerun;
+    return A;
+  }
+  bool fused_reduce(int cnt) const {
+    static const bool off = getenv("JFNK_FUSED_REDUCE") && atoi(getenv("JFNK_FUSED_REDUCE")) == 0;
+    return g_.nranks > 1 && p2p_ && cnt <= kP2PMaxScalars && !off;
+  }
+  void p2p_allreduce(int off, int cnt, int op, int givens_j, int taken, int rerun, int skippable = 0) {
+    P2PReduceArgs A = p2p_next_reduce(off, cnt, op, givens_j, taken, rerun, skippable);
     Prof prof(this, K_ALLREDUCE, 8.0 * cnt * g_.nranks);
     p2p_allreduce_kernel<<<1, kP2PMaxScalars, 0, stream_>>>(A);
   }
@@ -963,6 +1028,8 @@ class CudaOps : public DeviceOps {
   cudaStream_t stream_ = nullptr;
   double* S_ = nullptr;
   double* pinned_ = nullptr;
+  double* posted_pin_ = nullptr;                 // post_read / wait_read slots (8 doubles each)
+  cudaEvent_t posted_ev_[JF_MAXV + 2] = {};
   ReduceWs ws_ = {nullptr, nullptr};
   double* halo_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::map<const void*, int> occupancy_;

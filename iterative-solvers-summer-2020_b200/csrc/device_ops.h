@@ -63,6 +63,8 @@ struct KernelStat {
 struct PmaParams; // mesh_math.h
 
 class DeviceOps {
+ protected:
+  double posted_[JF_MAXV + 2][8]; // default post_read / wait_read storage (synchronous backends)
  public:
   virtual ~DeviceOps() {}
   virtual int64_t launches() const = 0;
@@ -90,6 +92,27 @@ class DeviceOps {
   virtual void allreduce_sum_givens(int off, int cnt, int j, int taken, int rerun) {
     allreduce_sum(off, cnt);
     givens(j, taken, rerun);
+  }
+
+  // ---- the Arnoldi loop without host round trips ------------------------------------------------------
+  // true: the operator / multi-dot / update kernels of this backend return at once while S[JS_STOP] is set, so the
+  // engine may enqueue Arnoldi step j+1 before it has seen the outcome of step j (Engine::cycle)
+  virtual bool can_speculate() const { return false; }
+  // enqueue a copy of S[off..off+cnt) into host slot `slot` (0 <= slot < JF_MAXV + 1, cnt <= 8) ...
+  virtual void post_read(int slot, int off, int cnt) { read_scalars(off, cnt, posted_[slot]); }
+  // ... and wait for exactly that copy (later work may still be running on the device)
+  virtual void wait_read(int slot, int cnt, double* host) { for (int i = 0; i < cnt; ++i) host[i] = posted_[slot][i]; }
+  // out[i] = V_i . w, out[nv] = w . w, summed over the slab ranks
+  virtual void mdot_reduced(int nv, const double* const* V, const double* w, int out_off) {
+    mdot(nv, V, w, out_off);
+    allreduce_sum(out_off, nv + 1);
+  }
+  // Gram-Schmidt update (as gs_update), ||w||^2 summed over the slab ranks into S[n2_off], then the Hessenberg / Givens
+  // step of column j (hd_math.h); `skippable`: part of a speculatively enqueued step
+  virtual void gs_update_givens(int nv, const double* const* V, double* w, int rd_off, int n2_off, int j, int taken,
+                                int rerun) {
+    gs_update(nv, V, w, rd_off, n2_off, -1);
+    allreduce_sum_givens(n2_off, 1, j, taken, rerun);
   }
 
   // ---- BLAS-1 on slab-local vectors of length grid.n() -------------------------------------------

@@ -431,16 +431,83 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
   const bool single = (grid_.nranks == 1);
   int nit = 0;
   double res = NAN;
+  // choice of z (_gcrotmk.py:96-105 with prepend_outer_v=True); the new Arnoldi vector goes to VS_[j]
+  auto choose = [&](int j) {
+    if (j < k) { zs[j] = OV_[ov_slots_[j]]; znidx[j] = JS_ZN2 + ov_slots_[j]; }
+    else if (j == k) { zs[j] = vs[0]; znidx[j] = JS_VN2 + 0; }
+    else { zs[j] = vs[j]; znidx[j] = JS_VN2 + j; }
+    vs[j + 1] = VS_[j];
+  };
+  auto clear_stop = [&]() { const double zero = 0.0; ops_->write_scalars(JS_STOP, 1, &zero); };
+  // Speculative mode: the Givens step of column j decides ON THE DEVICE whether the process goes on (converged to ptol,
+  // breakdown, non-finite, second Gram-Schmidt pass wanted -> JS_STOP), the host enqueues step j+1 before it waits for
+  // step j's record, and the kernels of a step enqueued after the stop return at once.  The stream never drains inside
+  // the loop and nothing that was not needed runs.  Needs kernels that honour JS_STOP (DeviceOps::can_speculate; the
+  // multi-kernel mesh residuals and preconditioner callbacks do not).
+  const bool spec = ops_->can_speculate() && !psolve_ && !is_mesh_problem(cfg_.problem);
+  {
+    const double ctl[3] = {0.0, spec ? ptol : -1.0, (spec && cfg_.gs_mode == JFNK_GS_CGS_IFNEEDED) ? tau2 : 0.0};
+    ops_->write_scalars(JS_STOP, 3, ctl); // JS_STOP, JS_PTOL, JS_TAU2
+  }
+  if (spec) {
+    auto enqueue_step = [&](int j) {
+      choose(j);
+      double* w = VS_[j];
+      apply_operator(zs[j], znidx[j], w, true);
+      // classical Gram-Schmidt against vs[0..j]: all dots in one fused reduction (all-reduced by the kernel's last CTA
+      // with slab ranks), then one fused update whose last CTA (all-reduces the norm and) runs the Givens step
+      ops_->mdot_reduced(j + 1, vs, w, JS_RD);
+      if (cfg_.gs_mode == JFNK_GS_CGS2) {
+        ops_->gs_update(j + 1, vs, w, JS_RD, JS_HN2A, -1);
+        ops_->allreduce_sum(JS_HN2A, 1);
+        ops_->mdot_reduced(j + 1, vs, w, JS_RD2);
+        ops_->gs_update_givens(j + 1, vs, w, JS_RD2, JS_HN2B, j, 1, 0);
+      } else {
+        ops_->gs_update_givens(j + 1, vs, w, JS_RD, JS_HN2A, j, 0, 0);
+      }
+      ops_->post_read(j, JS_REC + j * JF_REC_STRIDE, 5);
+    };
+    enqueue_step(0);
+    for (int j = 0; j < m; ++j) {
+      bool ahead = (j + 1 < m);
+      if (ahead) enqueue_step(j + 1); // dropped on the device if step j stops the process
+      double sc[5]; // w.w, ||w||^2 after pass 1, after pass 2, residual estimate, flags
+      ops_->wait_read(j, 5, sc);
+      int st = ops_->status();
+      if (st) { clear_stop(); return st; }
+      int flags = (int)sc[4];
+      bool second = (cfg_.gs_mode == JFNK_GS_CGS2);
+      if (flags & JF_FLAG_NEED_REORTH) {
+        // the first pass cancelled more than 1/tau: step j+1 was dropped; take the second pass of step j, redo its column
+        if (ahead) { nfev_--; ahead = false; }
+        clear_stop();
+        ops_->mdot_reduced(j + 1, vs, VS_[j], JS_RD2);
+        ops_->gs_update_givens(j + 1, vs, VS_[j], JS_RD2, JS_HN2B, j, 1, 1);
+        ops_->post_read(j, JS_REC + j * JF_REC_STRIDE, 5);
+        ops_->wait_read(j, 5, sc);
+        st = ops_->status();
+        if (st) { clear_stop(); return st; }
+        flags = (int)sc[4];
+        second = true;
+        const bool stops = (flags & (JF_FLAG_BREAKDOWN | JF_FLAG_NONFINITE)) || sc[3] < ptol;
+        if (!stops && j + 1 < m) { enqueue_step(j + 1); ahead = true; }
+      }
+      res = sc[3];
+      nit = j + 1;
+      inner_total_++;
+      if (second) reorth_total_++;
+      const bool stops = (flags & (JF_FLAG_BREAKDOWN | JF_FLAG_NONFINITE)) || res < ptol;
+      if (stops && ahead) nfev_--; // the step that was enqueued ahead never ran
+      if (flags & JF_FLAG_NONFINITE) { clear_stop(); return fail(JFNK_NONFINITE, "Function returned non-finite results"); }
+      if (stops) break;
+    }
+    clear_stop();
+  } else {
   for (int j = 0; j < m; ++j) {
-    // choice of z (_gcrotmk.py:96-105 with prepend_outer_v=True)
-    const double* z;
-    int zi;
-    if (j < k) { z = OV_[ov_slots_[j]]; zi = JS_ZN2 + ov_slots_[j]; }
-    else if (j == k) { z = vs[0]; zi = JS_VN2 + 0; }
-    else { z = vs[j]; zi = JS_VN2 + j; }
-    zs[j] = z; znidx[j] = zi;
+    choose(j);
+    const double* z = zs[j];
+    const int zi = znidx[j];
     double* w = VS_[j];
-    vs[j + 1] = w;
     if (psolve_ && op_tmp_) {
       // left preconditioning (_gcrotmk.py:113-121): w = M (A z)
       apply_operator(z, zi, op_tmp_, true);
@@ -453,41 +520,38 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
     // classical Gram-Schmidt against vs[0..j]: all dots in one fused reduction, then one fused update.
     // One host round-trip per Arnoldi step: {w.w, ||w||^2 after pass 1, residual estimate, flags}.  The host
     // decides from it whether a second (re-orthogonalisation) pass is needed; only then more work is enqueued.
-    ops_->mdot(j + 1, vs, w, JS_RD);
-    ops_->allreduce_sum(JS_RD, j + 2);
+    ops_->mdot_reduced(j + 1, vs, w, JS_RD);
     bool second = (cfg_.gs_mode == JFNK_GS_CGS2);
     double sc[5]; // JS_WW, JS_HN2A, JS_HN2B, JS_RES, JS_FLAGS
     if (!second) {
-      ops_->gs_update(j + 1, vs, w, JS_RD, JS_HN2A, single ? j : -1); // single GPU: Givens fused into the last CTA
-      if (!single) ops_->allreduce_sum_givens(JS_HN2A, 1, j, 0, 0);
+      ops_->gs_update_givens(j + 1, vs, w, JS_RD, JS_HN2A, j, 0, 0);
       ops_->read_scalars(JS_WW, 5, sc);
       second = (cfg_.gs_mode == JFNK_GS_CGS_IFNEEDED) && (sc[1] < tau2 * sc[0]);
       if (second) {
-        ops_->mdot(j + 1, vs, w, JS_RD2);
-        ops_->allreduce_sum(JS_RD2, j + 1);
-        ops_->gs_update(j + 1, vs, w, JS_RD2, JS_HN2B, -1);
-        ops_->allreduce_sum_givens(JS_HN2B, 1, j, 1, 1); // redo column j with h = (RD + RD2)/||V||, ||w|| from pass 2
+        ops_->mdot_reduced(j + 1, vs, w, JS_RD2);
+        ops_->gs_update_givens(j + 1, vs, w, JS_RD2, JS_HN2B, j, 1, 1); // redo column j with h = (RD + RD2)/||V||, ||w|| from pass 2
         ops_->read_scalars(JS_WW, 5, sc);
       }
     } else {
       ops_->gs_update(j + 1, vs, w, JS_RD, JS_HN2A, -1);
       ops_->allreduce_sum(JS_HN2A, 1);
-      ops_->mdot(j + 1, vs, w, JS_RD2);
-      ops_->allreduce_sum(JS_RD2, j + 1);
-      ops_->gs_update(j + 1, vs, w, JS_RD2, JS_HN2B, -1);
-      ops_->allreduce_sum_givens(JS_HN2B, 1, j, 1, 0);
+      ops_->mdot_reduced(j + 1, vs, w, JS_RD2);
+      ops_->gs_update_givens(j + 1, vs, w, JS_RD2, JS_HN2B, j, 1, 0);
       ops_->read_scalars(JS_WW, 5, sc);
     }
     int st = ops_->status();
-    if (st) return st;
+    if (st) { clear_stop(); return st; }
     res = sc[3];
     int flags = (int)sc[4];
     nit = j + 1;
     inner_total_++;
     if (second) reorth_total_++;
-    if (flags & JF_FLAG_NONFINITE) return fail(JFNK_NONFINITE, "Function returned non-finite results");
+    if (flags & JF_FLAG_NONFINITE) { clear_stop(); return fail(JFNK_NONFINITE, "Function returned non-finite results"); }
     if (res < ptol || (flags & JF_FLAG_BREAKDOWN)) break;
   }
+  clear_stop(); // (a breakdown sets it even in this mode)
+  }
+  (void)single;
   // y = lstsq(R, Q[0,:]) * inner_res_0 ; dx = sum zs_i y_i (lgmres.py:188,206-208)
   ops_->lsq(nit, znidx, JS_VN2 + 0);
   int slot = -1;
@@ -513,6 +577,7 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
 // scipy.sparse.linalg.lgmres with x0 = 0 (lgmres.py:124-232), general number of outer cycles.
 int Engine::lgmres_general(const double* b, double* x, double rtol, int maxiter, int* info, double* res_out,
                            int* inner_out) {
+  { const double zero = 0.0; ops_->write_scalars(JS_STOP, 1, &zero); } // (stale after an aborted solve)
   ops_->mdot(0, nullptr, b, JS_TMP0);
   ops_->allreduce_sum(JS_TMP0, 1);
   double bn2;
@@ -600,6 +665,7 @@ int Engine::newton(double* u, const jfnk_newton_opts* o, jfnk_history* hist) {
   if (maxiter <= 0) maxiter = (o->iter > 0) ? (int64_t)o->iter + 1 : 100 * ((int64_t)grid_.n_global() + 1);
 
   nfev_ = 0; inner_total_ = 0; reorth_total_ = 0;
+  { const double zero = 0.0; ops_->write_scalars(JS_STOP, 1, &zero); } // (stale after an aborted solve)
   if (hist) { hist->count = 0; hist->nfev = 0; hist->inner_iters = 0; hist->reorth = 0; }
 
   double* x = u;

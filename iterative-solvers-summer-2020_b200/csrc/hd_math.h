@@ -118,9 +118,18 @@ JF_HD void hess_givens_step(double* S, int j, int taken, int rerun) {
   double gj = g[j];
   g[j] = c * gj;
   g[j + 1] = -s * gj;
-  S[JS_RES] = fabs(g[j + 1]);
+  const double res = fabs(g[j + 1]);
+  S[JS_RES] = res;
   if (!isfinite(rr) || !isfinite(ww)) flags |= JF_FLAG_NONFINITE;
+  // the decisions the host would take from these scalars (engine.cpp, Engine::cycle), taken here so that work the host has
+  // already enqueued for the next Arnoldi step can be dropped on the device
+  const double tau2 = S[JS_TAU2];
+  if (!taken && tau2 > 0.0 && hn2 < tau2 * ww) flags |= JF_FLAG_NEED_REORTH;
+  const bool stop = (flags & (JF_FLAG_NEED_REORTH | JF_FLAG_BREAKDOWN | JF_FLAG_NONFINITE)) != 0 || res < S[JS_PTOL];
   S[JS_FLAGS] = (double)flags;
+  S[JS_STOP] = stop ? 1.0 : 0.0;
+  double* rec = S + JS_REC + (size_t)j * JF_REC_STRIDE;
+  rec[0] = ww; rec[1] = S[JS_HN2A]; rec[2] = taken ? S[JS_HN2B] : S[JS_HN2A]; rec[3] = res; rec[4] = (double)flags;
 }
 
 // y = R^{-1} g (nit x nit), y *= scale ; coef[i] = y[i] / sqrt(S[zn2_idx[i]])  (dx = sum coef_i Z_i with

@@ -8,7 +8,10 @@
 // Both replace an NCCL call (send/recv pair, ncclAllReduce) whose cost at these sizes (256 KiB, <= 50 doubles) is pure
 // launch + protocol latency.  Flags carry monotonically increasing epochs; payload buffers are double-buffered by
 // epoch parity, which is sufficient because a rank can run at most one exchange ahead of a peer (completing exchange
-// e needs the peer's contribution to e, which the peer sends only after it has consumed exchange e-1).
+// e needs the peer's contribution to e, which the peer sends only after it has consumed exchange e-1).  The all-reduce
+// mailboxes are FOUR deep (epoch & 3): kernels of a speculatively enqueued Arnoldi step that find JS_STOP set skip their
+// exchange on every rank alike, so up to two consecutive epochs may never be used and two live exchanges can be three
+// epochs apart.
 #pragma once
 #include "cuda_common.cuh"
 
@@ -93,11 +96,16 @@ struct P2PReduceArgs {
   const unsigned long long* my_flags;             // [nranks]
   unsigned long long epoch;
   int givens_j, givens_taken, givens_rerun;       // >= 0: run the Hessenberg/Givens step of column j afterwards
+  int skippable;                                  // part of the Arnoldi loop: dropped while S[JS_STOP] is set
   int* err;
 };
 
-__global__ void __launch_bounds__(kP2PMaxScalars) p2p_allreduce_kernel(P2PReduceArgs A) {
+// The all-reduce proper, run by ONE CTA of at least kP2PMaxScalars threads (all of its threads must call it).  Used by the
+// stand-alone kernel below and, fused, by the CTA that finalises the local sums of a multi-dot / Gram-Schmidt update
+// (blas_kernels.cuh): the collective then costs no launch of its own.
+__device__ __forceinline__ void p2p_allreduce_block(const P2PReduceArgs& A) {
   const int i = threadIdx.x;
+  __syncthreads(); // the local values S[off..] were written by other threads of this CTA
   if (i < A.cnt) {
     const double v = A.S[A.off + i];
     for (int q = 0; q < A.nranks; ++q) A.mailbox_peer[q][(size_t)A.rank * kP2PMaxScalars + i] = v;
@@ -121,6 +129,11 @@ __global__ void __launch_bounds__(kP2PMaxScalars) p2p_allreduce_kernel(P2PReduce
     __syncthreads();
     if (i == 0) hess_givens_step(A.S, A.givens_j, A.givens_taken, A.givens_rerun);
   }
+}
+
+__global__ void __launch_bounds__(kP2PMaxScalars) p2p_allreduce_kernel(P2PReduceArgs A) {
+  if (A.skippable && A.S[JS_STOP] != 0.0) return; // speculative Arnoldi work after the process stopped (every rank agrees)
+  p2p_allreduce_block(A);
 }
 
 } // namespace jfnk

@@ -34,11 +34,21 @@ enum ScalarSlot : int {
   JS_G = JS_SN + JF_MAXV,        // [JF_MAXV+1] rotated right-hand side
   JS_Y = JS_G + JF_MAXV + 1,     // [JF_MAXV]   LSQ solution
   JS_R = JS_Y + JF_MAXV,         // [JF_MAXV*JF_MAXV] upper-triangular factor, column-major R[i + j*JF_MAXV]
-  JS_COUNT = JS_R + JF_MAXV * JF_MAXV
+  // Device-side control of the Arnoldi loop.  The host enqueues Arnoldi step j+1 BEFORE it has seen the outcome of step j
+  // (it reads step j's record one step late, so the stream never drains); the Givens step of column j decides on the
+  // device whether the process goes on, and every kernel of the Arnoldi loop returns at once while JS_STOP is set.
+  JS_STOP = JS_R + JF_MAXV * JF_MAXV, // != 0: converged / breakdown / non-finite / a second Gram-Schmidt pass is wanted
+  JS_PTOL,                       // inner tolerance of the running cycle (host-written; < 0: never stop on the residual)
+  JS_TAU2,                       // tau^2 of the "cgs-ifneeded" test ||w_after||^2 < tau^2 w.w (0: never ask for a 2nd pass)
+  JS_pad4,
+  JS_REC,                        // [JF_MAXV][JF_REC_STRIDE] per-step records {w.w, HN2A, HN2B, RES, FLAGS}
+  JS_COUNT = JS_REC + JF_MAXV * 8
 };
+constexpr int JF_REC_STRIDE = 8;
 
 constexpr int JF_FLAG_BREAKDOWN = 1;
 constexpr int JF_FLAG_NONFINITE = 2;
-constexpr int JF_FLAG_REORTH = 4;
+constexpr int JF_FLAG_REORTH = 4;      // a second Gram-Schmidt pass was taken
+constexpr int JF_FLAG_NEED_REORTH = 8; // the first pass cancelled more than 1/tau: the host must enqueue the second pass
 
 } // namespace jfnk

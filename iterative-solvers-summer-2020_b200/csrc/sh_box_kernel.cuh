@@ -66,6 +66,7 @@ __device__ __forceinline__ void tma_prefetch_map(const CUtensorMap* map) {
 template <int OP, bool HAS_V>
 __global__ void __launch_bounds__(kBoxThreads, 2)
     sh_box_kernel(const __grid_constant__ ShBoxMaps maps, ShArgs A, ShBoxRows hr, SHParams P, double* S, ReduceWs ws) {
+  if (sh_is_operator<OP>() && S[JS_STOP] != 0.0) return; // (before the fused halo push: every rank skips alike)
   using LY = BoxLayout<OP, HAS_V>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stage0 = reinterpret_cast<double*>(smem_raw);
@@ -76,7 +77,16 @@ __global__ void __launch_bounds__(kBoxThreads, 2)
   const int npairs = nrows / kBoxR;
   const int strips = (nx + kBoxStrip - 1) / kBoxStrip;
   const long long total = (long long)strips * npairs; // work units: (strip, row pair), strip-major
-  const long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
+  long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
+  if (A.mode & 2) {
+    // band-major mapping: gridDim.x = strips * bands; the CTAs of a band sweep the same rows of all strips side by side,
+    // so the rows being read and written at any moment are few and whole (DRAM page locality of a linear sweep)
+    const int bands = gridDim.x / strips;
+    const int strip = blockIdx.x % strips, band = blockIdx.x / strips;
+    begin = (long long)strip * npairs + (long long)npairs * band / bands;
+    end = (long long)strip * npairs + (long long)npairs * (band + 1) / bands;
+  }
+  const bool cs = (A.mode & 1) != 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(kBoxThreads, 2)
             double2 o, o2 = zero2, o3 = zero2;
             o.x = sh_value<OP>(P, scale, u2.x, s1x, sdx, s2x, dv.x, fv.x, o2.x, o3.x, acc);
             o.y = sh_value<OP>(P, scale, u2.y, s1y, sdy, s2y, dv.y, fv.y, o2.y, o3.y, acc);
-            stg2(A.out + e, o);
+            if (cs) stg2_cs(A.out + e, o); else stg2(A.out + e, o);
             if ((OP == OP_RESID && A.out2) || OP == OP_LINPREP) stg2(A.out2 + e, o2);
             if (OP == OP_RESID && A.out3) stg2(A.out3 + e, o3);
           }

@@ -42,6 +42,7 @@ struct ShArgs {
   double* out3;                  // RESID: G(x + a v) = F + d (may be null): what OP_JVPG subtracts once this point is accepted
   int nx, nrows;
   int norm_off;                  // RESID: S[norm_off..+2] = sum F^2, max|F|, max|t|
+  int mode;                      // sh_box_kernel tuning bits: 1 = streaming (evict-first) stores, 2 = band-major CTA mapping
   // Fused halo exchange over peer memory (marching kernel, slab ranks): the kernel itself stores the first / last two rows of
   // `push_field` (1: x, 2: v) into the neighbours' halo buffers, raises their arrival flags, and its producer lane waits for
   // this rank's own flags only at the moment it needs a halo row -- the exchange overlaps the interior rows.  0 = off.
@@ -97,11 +98,16 @@ __device__ __forceinline__ double sh_scale(const ShArgs& A, const double* S) {
   return 1.0;
 }
 
+// the passes that are the Jacobian / linear operator inside the Arnoldi loop: they return at once while JS_STOP is set
+template <int OP>
+__host__ __device__ constexpr bool sh_is_operator() { return OP == OP_JVP || OP == OP_JVPG || OP == OP_LINMV; }
+
 // ---------------------------------------------------------------------------------------------------
 // one thread per point
 // ---------------------------------------------------------------------------------------------------
 template <int OP, bool HAS_V>
 __global__ void __launch_bounds__(256) sh_point_kernel(ShArgs A, SHParams P, double* S, ReduceWs ws) {
+  if (sh_is_operator<OP>() && S[JS_STOP] != 0.0) return; // speculatively enqueued Arnoldi step after the process stopped
   const int nx = A.nx, nrows = A.nrows;
   const size_t n = (size_t)nx * nrows;
   const double a = HAS_V ? eval_sref(S, A.a) : 0.0;
@@ -194,6 +200,7 @@ struct TmaWork {
 
 template <int OP, bool HAS_V>
 __global__ void __launch_bounds__(kTmaThreads) sh_tma_kernel(ShArgs A, SHParams P, double* S, ReduceWs ws) {
+  if (sh_is_operator<OP>() && S[JS_STOP] != 0.0) return; // (before the fused halo push: every rank skips alike)
   using LY = TmaLayout<OP, HAS_V>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stage0 = reinterpret_cast<double*>(smem_raw);

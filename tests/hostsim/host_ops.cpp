@@ -36,10 +36,14 @@ class HostOps : public DeviceOps {
 
   void read_scalars(int off, int cnt, double* host) override { memcpy(host, &S_[off], sizeof(double) * cnt); }
   void write_scalars(int off, int cnt, const double* host) override { memcpy(&S_[off], host, sizeof(double) * cnt); }
-  void allreduce_sum(int off, int cnt) override { if (g_.nranks > 1) ar_(user_, &S_[off], cnt, 0); }
+  // (a collective of a speculatively enqueued Arnoldi step is dropped with the step: every rank sees the same JS_STOP)
+  void allreduce_sum(int off, int cnt) override { if (g_.nranks > 1 && !stopped()) ar_(user_, &S_[off], cnt, 0); }
   void allreduce_max(int off, int cnt) override { if (g_.nranks > 1) ar_(user_, &S_[off], cnt, 1); }
 
+  bool can_speculate() const override { return !(getenv("JFNK_SPECULATE") && atoi(getenv("JFNK_SPECULATE")) == 0); }
+  bool stopped() const { return S_[JS_STOP] != 0.0; } // what the CUDA kernels of the Arnoldi loop check first
   void mdot(int nv, const double* const* V, const double* w, int out_off) override {
+    if (stopped()) return;
     launches_++;
     size_t n = g_.n();
     for (int i = 0; i < nv; ++i) {
@@ -52,6 +56,7 @@ class HostOps : public DeviceOps {
     S_[out_off + nv] = acc;
   }
   void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int fuse_givens_j) override {
+    if (stopped()) return;
     launches_++;
     size_t n = g_.n();
     std::vector<double> c(nv);
@@ -119,7 +124,11 @@ class HostOps : public DeviceOps {
     for (size_t e = 0; e < g_.n(); ++e) m = fmax(m, fabs(v[e]));
     S_[out_off] = m;
   }
-  void givens(int j, int taken, int rerun) override { launches_++; hess_givens_step(S_.data(), j, taken, rerun); }
+  void givens(int j, int taken, int rerun) override {
+    if (stopped()) return;
+    launches_++;
+    hess_givens_step(S_.data(), j, taken, rerun);
+  }
   void lsq(int nit, const int* zn2_idx, int scale_n2_idx) override { launches_++; lsq_solve(S_.data(), nit, zn2_idx, scale_n2_idx); }
 
   // ---- Swift-Hohenberg ---------------------------------------------------------------------------
@@ -212,6 +221,7 @@ class HostOps : public DeviceOps {
   void sh_bind_x0(const double*) override {}
   void sh_jvp(const double* x0, const double* z, ScalarRef sc, ScalarRef div, const double* d, const double* f0,
               const double* g0, double* w) override {
+    if (stopped()) return;
     launches_++;
     std::vector<double> t, top, bot;
     combined(x0, z, eval_sref(S_.data(), sc), t, top, bot);
@@ -241,6 +251,7 @@ class HostOps : public DeviceOps {
       }
   }
   void shlin_matvec(const double* z, ScalarRef a, const double* D, double* w) override {
+    if (stopped()) return;
     launches_++;
     std::vector<double> top, bot;
     halos(z, top, bot);

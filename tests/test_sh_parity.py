@@ -419,3 +419,31 @@ def test_callback_exception_propagates_like_scipy(buffers):
     assert len(calls) == 1  # the solve stopped at once
     # the context is still usable afterwards
     assert rel(jf.newton_krylov(F, Uo), jf.newton_krylov(F, Uo)) == 0.0
+
+
+@pytest.mark.parametrize("gs,tau", [("cgs-ifneeded", 0.25), ("cgs-ifneeded", 0.97), ("cgs2", 0.25), ("cgs", 0.25)])
+def test_speculative_arnoldi_loop_is_bitwise_the_synchronous_one(buffers, monkeypatch, gs, tau):
+    """The engine enqueues Arnoldi step j+1 before it has read the outcome of step j; the device drops it (JS_STOP) when
+    step j converged, broke down or asked for a second Gram-Schmidt pass.  Same arithmetic in the same order as the loop
+    that reads back after every step (JFNK_SPECULATE=0): identical bits, identical counts of residual evaluations, inner
+    iterations and second passes (tau = 0.97 forces a second pass on most steps)."""
+    N = 64
+    U0 = seeded_state(N)
+    out = {}
+    for spec in ("1", "0"):
+        monkeypatch.setenv("JFNK_SPECULATE", spec)
+        F = jf.SHResidual(N=N, buffers=buffers, gs=gs, gs_tau=tau)
+        hist = []
+        U = F.steps(U0, 3, history=hist)
+        out[spec] = (U, [(h["nit"], h["nfev"], h["inner_iters"], h["reorth"]) for h in hist])
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert out["1"][1] == out["0"][1]
+    if gs == "cgs-ifneeded" and tau > 0.9:
+        assert sum(c[3] for c in out["1"][1]) > 10  # the second-pass path was exercised
+    # the linear solver entry point (several outer cycles) too
+    S = jf.SHLinearised(N=N, buffers=buffers, gs=gs, gs_tau=tau)
+    lin = {}
+    for spec in ("1", "0"):
+        monkeypatch.setenv("JFNK_SPECULATE", spec)
+        lin[spec] = S.steps(0.1 * U0, nsteps=2)[0]
+    assert np.array_equal(lin["1"], lin["0"])
