@@ -21,6 +21,7 @@
 #include "p2p_kernels.cuh"
 #include "sh_kernels.cuh"
 #include "sh_box_kernel.cuh"
+#include "sh_cycle.cuh"
 
 namespace jfnk {
 
@@ -30,10 +31,10 @@ inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 // kernel classes of the per-kernel timing (bench.py roofline); bytes are the ALGORITHMIC bytes of DESIGN.md
 enum KClass { K_MDOT = 0, K_GS_UPDATE, K_MAXPY, K_LINCOMB, K_SPMV_LAP, K_SPMV_L, K_SET_PREV, K_RESIDUAL, K_JVP,
-              K_SHLIN, K_MESH, K_SCALAR, K_MDOT2, K_GS_UPDATE2, K_HALO, K_ALLREDUCE, K_COUNT };
+              K_SHLIN, K_MESH, K_SCALAR, K_MDOT2, K_GS_UPDATE2, K_HALO, K_ALLREDUCE, K_CYCLE, K_COUNT };
 const char* const kClassName[K_COUNT] = {"mdot", "gs_update", "maxpy", "lincomb", "spmv_lap", "spmv_L", "set_prev",
                                          "sh_residual", "sh_jvp", "shlin", "mesh", "scalar", "mdot_pass2",
-                                         "gs_update_pass2", "halo_exchange", "allreduce"};
+                                         "gs_update_pass2", "halo_exchange", "allreduce", "lgmres_cycle"};
 
 class CudaOps : public DeviceOps {
  public:
@@ -367,6 +368,74 @@ class CudaOps : public DeviceOps {
     for (int i = 0; i < JF_MAXV; ++i) L.v[i] = i < nit ? zn2_idx[i] : 0;
     Prof prof(this, K_SCALAR, 0.0);
     lsq_kernel<<<1, 1, 0, stream_>>>(S_, nit, L, scale_n2_idx);
+  }
+
+  // ---- whole LGMRES cycle in one launch (sh_cycle.cuh): small single-rank Swift-Hohenberg grids -----------------------
+  template <int OP>
+  int cycle_cluster(const CycleLayout& Lmax) {
+    int& cs = cycle_cluster_[OP == OP_JVPG ? 0 : 1];
+    if (cs != 0) return cs;
+    cs = -1;
+    if (cudaFuncSetAttribute(sh_cycle_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lmax.total) == cudaSuccess) {
+      cudaFuncSetAttribute(sh_cycle_kernel<OP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cycle_c_); cfg.blockDim = dim3(kCycThreads); cfg.dynamicSmemBytes = Lmax.total;
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = cycle_c_; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, sh_cycle_kernel<OP>, &cfg) == cudaSuccess && nclusters >= 1) cs = cycle_c_;
+    }
+    cudaGetLastError();
+    return cs;
+  }
+  bool cycle_fused(const FusedCycleIn& in, FusedCycleOut& out) override {
+    const char* env = getenv("JFNK_CYCLE_FUSED"); // (read per cycle: the parity tests flip it)
+    const bool off = env && atoi(env) == 0;
+    if (off || variant_ != 0 || g_.nranks != 1 || capturing_ || in.m_max + 1 > JF_MAXV) return false;
+    // cluster size: 16 CTAs when every CTA gets at least one row and the bands fit, else 8
+    if (cycle_c_ == 0) {
+      cycle_c_ = -1;
+      for (int c : {16, 8}) {
+        if (g_.ny < c) continue;
+        const int rmax = (g_.ny + c - 1) / c;
+        CycleLayout L(((rmax * g_.nx + 3) & ~3), (rmax + 4) * g_.nx, in.m_max);
+        if (L.total > (size_t)226 * 1024) continue;
+        cycle_c_ = c; cycle_pitch_ = (rmax * g_.nx + 3) & ~3; cycle_ext_ = (rmax + 4) * g_.nx;
+        break;
+      }
+    }
+    if (cycle_c_ < 0) return false;
+    const CycleLayout Lmax(cycle_pitch_, cycle_ext_, in.m_max);
+    const int cs = in.linear ? cycle_cluster<OP_LINMV>(Lmax) : cycle_cluster<OP_JVPG>(Lmax);
+    if (cs < 0) return false;
+    CycleArgs A;
+    memset(&A, 0, sizeof(A));
+    A.nx = g_.nx; A.ny = g_.ny; A.m = in.m; A.k = in.k; A.gs_mode = in.gs_mode;
+    A.pitch = cycle_pitch_; A.ext = cycle_ext_;
+    A.omega = in.omega; A.ptol = in.ptol; A.tau2 = in.tau2; A.v0n2 = in.v0n2;
+    A.x0 = in.x0; A.g0 = in.g0; A.v0 = in.v0;
+    for (int j = 0; j < in.k; ++j) { A.ov[j] = in.ov[j]; A.ov_zn2[j] = in.ov_zn2[j]; }
+    A.out = in.out; A.out_zn2 = in.out_zn2; A.S = S_;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kCycThreads);
+    cfg.dynamicSmemBytes = CycleLayout(cycle_pitch_, cycle_ext_, in.m).total; cfg.stream = stream_;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = cs; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    {
+      // per Arnoldi step j: operator 4 vectors, Gram-Schmidt 2j + 3 -- all from shared memory; HBM sees x0, g0, v0, dx once
+      Prof prof(this, K_CYCLE, nb(4.0 + in.k));
+      bool ok = in.linear ? ck(cudaLaunchKernelEx(&cfg, sh_cycle_kernel<OP_LINMV>, A, shp_), "cudaLaunchKernelEx(sh_cycle)")
+                          : ck(cudaLaunchKernelEx(&cfg, sh_cycle_kernel<OP_JVPG>, A, shp_), "cudaLaunchKernelEx(sh_cycle)");
+      if (!ok) return true; // (status() reports the launch error)
+    }
+    double rec[5] = {0, 0, 0, 0, 0};
+    read_scalars(JS_CYC, 5, rec);
+    out.nit = (int)rec[0]; out.reorth = (int)rec[1]; out.res = rec[2]; out.flags = (int)rec[3]; out.dxn2 = rec[4];
+    return true;
   }
 
   // ---- Swift-Hohenberg ------------------------------------------------------------------------------
@@ -1052,6 +1121,8 @@ class CudaOps : public DeviceOps {
   int64_t capture_launch0_ = 0, graph_replays_ = 0;
   cudaGraphExec_t graph_exec_ = nullptr;
   int relax_cluster_ = 0; // 0 untried, -1 unavailable, else the cluster size of pma_relax_kernel
+  int cycle_c_ = 0, cycle_pitch_ = 0, cycle_ext_ = 0; // sh_cycle_kernel: cluster size that fits (0 untried, -1 none), band sizes
+  int cycle_cluster_[2] = {0, 0};                     // per operator: cluster size the device can schedule (-1: cannot)
   cudaStream_t cap_stream_ = nullptr, user_stream_ = nullptr;
   bool p2p_ = false;
   void* p2p_block_ = nullptr;

@@ -62,6 +62,25 @@ struct KernelStat {
 
 struct PmaParams; // mesh_math.h
 
+// One whole LGMRES inner cycle in one launch (Engine::cycle -> DeviceOps::cycle_fused; CUDA: sh_cycle.cuh)
+struct FusedCycleIn {
+  int linear;            // 0: FD Jacobian of the Swift-Hohenberg residual about x0 ; 1: the linearly-implicit operator
+  const double* x0;      // linearisation point (null when linear)
+  const double* g0;      // G(x0) ; linear: the diagonal D
+  const double* v0;      // unnormalised start vector
+  double v0n2, omega, ptol, tau2;
+  int gs_mode, m, k;     // m = inner_m + k Arnoldi steps at most, k augmentation vectors in use
+  int m_max;             // inner_m + outer_k
+  const double* ov[JF_MAXOV]; // the augmentation vectors in use, oldest first ...
+  int ov_zn2[JF_MAXOV];       // ... and the arena index of their squared norms
+  double* out;           // dx
+  int out_zn2;           // arena index that receives ||dx||^2
+};
+struct FusedCycleOut {
+  int nit, reorth, flags;
+  double res, dxn2;
+};
+
 class DeviceOps {
  protected:
   double posted_[JF_MAXV + 2][8]; // default post_read / wait_read storage (synchronous backends)
@@ -114,6 +133,10 @@ class DeviceOps {
     gs_update(nv, V, w, rd_off, n2_off, -1);
     allreduce_sum_givens(n2_off, 1, j, taken, rerun);
   }
+
+  // The whole cycle -- Arnoldi process with classical Gram-Schmidt, Givens QR, least squares, dx = sum y_i z_i -- as one
+  // launch, when the backend has such a kernel for this grid (small single-rank Swift-Hohenberg grids); false = not done.
+  virtual bool cycle_fused(const FusedCycleIn& /*in*/, FusedCycleOut& /*out*/) { return false; }
 
   // ---- BLAS-1 on slab-local vectors of length grid.n() -------------------------------------------
   // out[i] = V_i . w (i < nv), out[nv] = w . w

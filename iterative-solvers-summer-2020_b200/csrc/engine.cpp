@@ -439,6 +439,36 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
     vs[j + 1] = VS_[j];
   };
   auto clear_stop = [&]() { const double zero = 0.0; ops_->write_scalars(JS_STOP, 1, &zero); };
+  // the ring slot the assembled correction goes to
+  int slot = -1;
+  for (int s = 0; s < (int)OV_.size(); ++s) {
+    if (std::find(ov_slots_.begin(), ov_slots_.end(), s) == ov_slots_.end()) { slot = s; break; }
+  }
+  double dxn2 = 0.0;
+  // Reference-sized Swift-Hohenberg grids: the whole cycle (Arnoldi process, least squares, dx assembly) is ONE launch of a
+  // single thread-block cluster that keeps the basis in shared memory (sh_cycle.cuh); the host reads one record.
+  bool fused = false;
+  if (!psolve_ && (cfg_.problem == JFNK_PROBLEM_SH || linear_op_) && (linear_op_ || g0_)) {
+    FusedCycleIn in;
+    memset(&in, 0, sizeof(in));
+    in.linear = linear_op_ ? 1 : 0;
+    in.x0 = linear_op_ ? nullptr : x0_;
+    in.g0 = linear_op_ ? D_ : g0_;
+    in.v0 = v0vec; in.v0n2 = v0n2; in.omega = omega_; in.ptol = ptol; in.tau2 = tau2;
+    in.gs_mode = cfg_.gs_mode; in.m = m; in.k = k; in.m_max = cfg_.inner_m + cfg_.outer_k;
+    for (int j = 0; j < k; ++j) { in.ov[j] = OV_[ov_slots_[j]]; in.ov_zn2[j] = JS_ZN2 + ov_slots_[j]; }
+    in.out = OV_[slot]; in.out_zn2 = JS_ZN2 + slot;
+    FusedCycleOut fo;
+    if (ops_->cycle_fused(in, fo)) {
+      int st = ops_->status();
+      if (st) return st;
+      fused = true;
+      nit = fo.nit; res = fo.res; dxn2 = fo.dxn2;
+      nfev_ += nit; inner_total_ += nit; reorth_total_ += fo.reorth;
+      if (fo.flags & JF_FLAG_NONFINITE) return fail(JFNK_NONFINITE, "Function returned non-finite results");
+    }
+  }
+  if (!fused) {
   // Speculative mode: the Givens step of column j decides ON THE DEVICE whether the process goes on (converged to ptol,
   // breakdown, non-finite, second Gram-Schmidt pass wanted -> JS_STOP), the host enqueues step j+1 before it waits for
   // step j's record, and the kernels of a step enqueued after the stop return at once.  The stream never drains inside
@@ -554,14 +584,10 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
   (void)single;
   // y = lstsq(R, Q[0,:]) * inner_res_0 ; dx = sum zs_i y_i (lgmres.py:188,206-208)
   ops_->lsq(nit, znidx, JS_VN2 + 0);
-  int slot = -1;
-  for (int s = 0; s < (int)OV_.size(); ++s) {
-    if (std::find(ov_slots_.begin(), ov_slots_.end(), s) == ov_slots_.end()) { slot = s; break; }
-  }
   ops_->maxpy(nit, zs, OV_[slot], JS_ZN2 + slot);
   ops_->allreduce_sum(JS_ZN2 + slot, 1);
-  double dxn2;
   ops_->read_scalars(JS_ZN2 + slot, 1, &dxn2);
+  } // !fused
   out.sol = OV_[slot];
   out.sol_slot = slot;
   out.sol_n2 = dxn2;

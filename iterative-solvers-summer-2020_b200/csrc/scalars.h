@@ -42,7 +42,10 @@ enum ScalarSlot : int {
   JS_TAU2,                       // tau^2 of the "cgs-ifneeded" test ||w_after||^2 < tau^2 w.w (0: never ask for a 2nd pass)
   JS_pad4,
   JS_REC,                        // [JF_MAXV][JF_REC_STRIDE] per-step records {w.w, HN2A, HN2B, RES, FLAGS}
-  JS_COUNT = JS_REC + JF_MAXV * 8
+  // outcome of a whole Arnoldi cycle run by ONE launch (sh_cycle.cuh): {inner iterations, second Gram-Schmidt passes,
+  // residual estimate, flags of the last column, ||dx||^2, 0, 0, 0} -> the host's single read-back per cycle
+  JS_CYC = JS_REC + JF_MAXV * 8,
+  JS_COUNT = JS_CYC + 8
 };
 constexpr int JF_REC_STRIDE = 8;
 

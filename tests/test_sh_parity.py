@@ -430,6 +430,7 @@ def test_speculative_arnoldi_loop_is_bitwise_the_synchronous_one(buffers, monkey
     N = 64
     U0 = seeded_state(N)
     out = {}
+    monkeypatch.setenv("JFNK_CYCLE_FUSED", "0")  # (at this size the default is the one-launch cycle kernel)
     for spec in ("1", "0"):
         monkeypatch.setenv("JFNK_SPECULATE", spec)
         F = jf.SHResidual(N=N, buffers=buffers, gs=gs, gs_tau=tau)
@@ -447,3 +448,41 @@ def test_speculative_arnoldi_loop_is_bitwise_the_synchronous_one(buffers, monkey
         monkeypatch.setenv("JFNK_SPECULATE", spec)
         lin[spec] = S.steps(0.1 * U0, nsteps=2)[0]
     assert np.array_equal(lin["1"], lin["0"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [61, 64, 40, 24])
+@pytest.mark.parametrize("gs,tau", [("cgs-ifneeded", 0.25), ("cgs-ifneeded", 0.97), ("cgs2", 0.25), ("cgs", 0.25)])
+def test_one_launch_cycle_kernel_matches_streaming_path(monkeypatch, N, gs, tau):
+    """Reference-sized grids run a whole LGMRES cycle (_gcrotmk.py:16-183 + lgmres.py:188-208) as one launch of a single
+    thread-block cluster with the basis in shared memory (csrc/sh_cycle.cuh).  Same point formulas, Givens / least-squares
+    functions and decisions as the streaming kernels (JFNK_CYCLE_FUSED=0); only the summation order of the dots differs, so
+    the Newton / inner iteration counts agree and the fields agree far inside the 1e-8 field criterion."""
+    U0 = seeded_state(N)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("JFNK_CYCLE_FUSED", fused)
+        F = jf.SHResidual(N=N, gs=gs, gs_tau=tau)
+        hist = []
+        U = F.steps(U0, 6, history=hist)
+        out[fused] = (U, [h["nit"] for h in hist], [h["inner_iters"] for h in hist], sum(h["reorth"] for h in hist),
+                      F.context().launches())
+    assert out["1"][1] == out["0"][1]
+    assert all(abs(a - b) <= 2 for a, b in zip(out["1"][2], out["0"][2]))
+    assert rel(out["1"][0], out["0"][0]) < 1e-9
+    assert out["1"][4] < out["0"][4] / 4  # one launch per cycle instead of three per Arnoldi step
+    if gs == "cgs2" or tau > 0.9:
+        assert out["1"][3] > 10  # the second-pass path of the cycle kernel was exercised
+    # against the SciPy oracle: the same bar as the streaming path
+    o = SHOracle(N=N)
+    href = []
+    Ur = o.run(U0, 6, history=href)
+    assert rel(out["1"][0], Ur) < 1e-8
+    assert out["1"][1] == [len(h["iters"]) for h in href]
+    # the linearly-implicit operator through the same kernel (several outer cycles per solve, rtol 1e-13)
+    lin = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("JFNK_CYCLE_FUSED", fused)
+        S = jf.SHLinearised(N=N, gs=gs, gs_tau=tau)
+        lin[fused] = S.steps(0.1 * U0, nsteps=3)[0]
+    assert rel(lin["1"], lin["0"]) < 1e-10
