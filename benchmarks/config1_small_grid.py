@@ -38,10 +38,18 @@ def main():
         Ur = o.run(U0, 40, history=href)
         tr = time.perf_counter() - t0
         err = np.linalg.norm(Ue.cpu().numpy() - Ur) / np.linalg.norm(Ur)
+        # where the device time goes (separate, instrumented pass: CUDA events around every launch)
+        F.profile(True)
+        F.steps(U.clone(), 40, inplace=True)
+        torch.cuda.synchronize()
+        prof = {k: {"launches": v["launches"], "us_per_launch": round(1e3 * v["ms"] / max(1, v["launches"]), 2),
+                    "ms_per_step": round(v["ms"] / 40, 4)} for k, v in F.profile_read().items()}
+        F.profile(False)
         print(json.dumps({"N": N, "steps": 40, "engine_steps_per_s": round(40 / te, 1), "scipy_steps_per_s": round(40 / tr, 1),
                           "rel_l2_after_40_steps": err, "f_evals_per_step": {"engine": float(np.mean([h["nfev"] for h in hist])),
                                                                               "scipy": float(np.mean([h["nfev"] for h in href]))},
-                          "newton_its_equal": [h["nit"] for h in hist] == [len(h["iters"]) for h in href]}), flush=True)
+                          "newton_its_equal": [h["nit"] for h in hist] == [len(h["iters"]) for h in href],
+                          "launches_per_step": F.context().launches() / 83.0, "kernels": prof}), flush=True)
 
 
 if __name__ == "__main__":

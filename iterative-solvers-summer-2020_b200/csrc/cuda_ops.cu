@@ -78,6 +78,15 @@ class CudaOps : public DeviceOps {
   ~CudaOps() override {
     if (graph_exec_) { cudaStreamSynchronize(stream_); cudaGraphExecDestroy(graph_exec_); }
     if (cap_stream_) cudaStreamDestroy(cap_stream_);
+    if (cycle_prof_) { // JFNK_CYCLE_PROF=1: where the one-launch cycle kernel spends its clock cycles
+      long long h[CP_COUNT] = {0};
+      cudaStreamSynchronize(stream_);
+      cudaMemcpy(h, cycle_prof_, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[jfnk cycle prof] cycles=%lld steps=%lld clocks: total=%lld load=%lld build=%lld apply=%lld dots=%lld "
+                      "update=%lld givens=%lld assemble=%lld\n", h[CP_CYCLES], h[CP_STEPS], h[CP_TOTAL], h[CP_LOAD], h[CP_BUILD],
+              h[CP_APPLY], h[CP_DOTS], h[CP_UPDATE], h[CP_GIVENS], h[CP_ASSEMBLE]);
+      cudaFree(cycle_prof_);
+    }
     p2p_teardown();
     if (comm_ && nccl_) nccl_->CommDestroy(comm_);
     for (auto& r : recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -418,6 +427,12 @@ class CudaOps : public DeviceOps {
     A.x0 = in.x0; A.g0 = in.g0; A.v0 = in.v0;
     for (int j = 0; j < in.k; ++j) { A.ov[j] = in.ov[j]; A.ov_zn2[j] = in.ov_zn2[j]; }
     A.out = in.out; A.out_zn2 = in.out_zn2; A.S = S_;
+    const bool trial = !in.linear && in.d && in.trial_x && in.trial_F && in.trial_G;
+    if (trial) { A.d = in.d; A.trial_x = in.trial_x; A.trial_F = in.trial_F; A.trial_G = in.trial_G; A.trial_norm_off = in.trial_norm_off; }
+    if (!cycle_prof_ && getenv("JFNK_CYCLE_PROF") && atoi(getenv("JFNK_CYCLE_PROF")) != 0 &&
+        cudaMalloc(&cycle_prof_, sizeof(long long) * CP_COUNT) == cudaSuccess)
+      cudaMemsetAsync(cycle_prof_, 0, sizeof(long long) * CP_COUNT, stream_);
+    A.prof = cycle_prof_;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kCycThreads);
     cfg.dynamicSmemBytes = CycleLayout(cycle_pitch_, cycle_ext_, in.m).total; cfg.stream = stream_;
@@ -427,14 +442,16 @@ class CudaOps : public DeviceOps {
     cfg.attrs = &at; cfg.numAttrs = 1;
     {
       // per Arnoldi step j: operator 4 vectors, Gram-Schmidt 2j + 3 -- all from shared memory; HBM sees x0, g0, v0, dx once
-      Prof prof(this, K_CYCLE, nb(4.0 + in.k));
+      Prof prof(this, K_CYCLE, nb(4.0 + in.k + (trial ? 4.0 : 0.0)));
       bool ok = in.linear ? ck(cudaLaunchKernelEx(&cfg, sh_cycle_kernel<OP_LINMV>, A, shp_), "cudaLaunchKernelEx(sh_cycle)")
                           : ck(cudaLaunchKernelEx(&cfg, sh_cycle_kernel<OP_JVPG>, A, shp_), "cudaLaunchKernelEx(sh_cycle)");
       if (!ok) return true; // (status() reports the launch error)
     }
-    double rec[5] = {0, 0, 0, 0, 0};
-    read_scalars(JS_CYC, 5, rec);
+    double rec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    read_scalars(JS_CYC, 8, rec);
     out.nit = (int)rec[0]; out.reorth = (int)rec[1]; out.res = rec[2]; out.flags = (int)rec[3]; out.dxn2 = rec[4];
+    out.has_trial = trial ? 1 : 0;
+    out.trial_nrm[0] = rec[5]; out.trial_nrm[1] = rec[6]; out.trial_nrm[2] = rec[7];
     return true;
   }
 
@@ -1122,6 +1139,7 @@ class CudaOps : public DeviceOps {
   cudaGraphExec_t graph_exec_ = nullptr;
   int relax_cluster_ = 0; // 0 untried, -1 unavailable, else the cluster size of pma_relax_kernel
   int cycle_c_ = 0, cycle_pitch_ = 0, cycle_ext_ = 0; // sh_cycle_kernel: cluster size that fits (0 untried, -1 none), band sizes
+  long long* cycle_prof_ = nullptr;
   int cycle_cluster_[2] = {0, 0};                     // per operator: cluster size the device can schedule (-1: cannot)
   cudaStream_t cap_stream_ = nullptr, user_stream_ = nullptr;
   bool p2p_ = false;

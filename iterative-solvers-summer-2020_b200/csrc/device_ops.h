@@ -75,10 +75,17 @@ struct FusedCycleIn {
   int ov_zn2[JF_MAXOV];       // ... and the arena index of their squared norms
   double* out;           // dx
   int out_zn2;           // arena index that receives ||dx||^2
+  // optional (d != null): also evaluate the full-step trial point of the Newton iteration that follows,
+  // t = x0 - dx -> trial_x, F(t) -> trial_F, G(t) -> trial_G, {sum F^2, max|F|, max|t|} -> S[trial_norm_off..+2]
+  const double* d;
+  double *trial_x, *trial_F, *trial_G;
+  int trial_norm_off;
 };
 struct FusedCycleOut {
   int nit, reorth, flags;
   double res, dxn2;
+  int has_trial;         // the trial point was evaluated; its norms:
+  double trial_nrm[3];
 };
 
 class DeviceOps {

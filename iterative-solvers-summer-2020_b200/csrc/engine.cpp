@@ -458,7 +458,12 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
     in.gs_mode = cfg_.gs_mode; in.m = m; in.k = k; in.m_max = cfg_.inner_m + cfg_.outer_k;
     for (int j = 0; j < k; ++j) { in.ov[j] = OV_[ov_slots_[j]]; in.ov_zn2[j] = JS_ZN2 + ov_slots_[j]; }
     in.out = OV_[slot]; in.out_zn2 = JS_ZN2 + slot;
+    trial_.valid = false;
+    if (trial_.want && !linear_op_) {
+      in.d = D_; in.trial_x = trial_.xt; in.trial_F = trial_.Ft; in.trial_G = trial_.Gt; in.trial_norm_off = JS_F2_B;
+    }
     FusedCycleOut fo;
+    memset(&fo, 0, sizeof(fo));
     if (ops_->cycle_fused(in, fo)) {
       int st = ops_->status();
       if (st) return st;
@@ -466,8 +471,10 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
       nit = fo.nit; res = fo.res; dxn2 = fo.dxn2;
       nfev_ += nit; inner_total_ += nit; reorth_total_ += fo.reorth;
       if (fo.flags & JF_FLAG_NONFINITE) return fail(JFNK_NONFINITE, "Function returned non-finite results");
+      if (fo.has_trial) { trial_.valid = true; for (int i = 0; i < 3; ++i) trial_.nrm[i] = fo.trial_nrm[i]; }
     }
   }
+  trial_.want = false;
   if (!fused) {
   // Speculative mode: the Givens step of column j decides ON THE DEVICE whether the process goes on (converged to ptol,
   // breakdown, non-finite, second Gram-Schmidt pass wanted -> JS_STOP), the host enqueues step j+1 before it waits for
@@ -754,9 +761,12 @@ int Engine::newton(double* u, const jfnk_newton_opts* o, jfnk_history* hist) {
       rc = cycle(Ft, v0n2, ptol, co);
       op_tmp_ = nullptr;
     } else {
+      // (a backend that runs the whole cycle in one launch may evaluate the full-step trial point in the same launch)
+      trial_.want = true; trial_.xt = xt; trial_.Ft = Ft; trial_.Gt = Gt;
       rc = cycle(Fx, f2, ptol, co);
     }
-    if (rc) return rc;
+    trial_.want = false;
+    if (rc) { trial_.valid = false; return rc; }
     if (co.sol_n2 == 0.0)
       return fail(JFNK_ZERO_STEP, "Jacobian inversion yielded zero vector. This indicates a bug in the Jacobian approximation.");
     const double* sol = co.sol; // Newton direction dx = -sol
@@ -771,7 +781,15 @@ int Engine::newton(double* u, const jfnk_newton_opts* o, jfnk_history* hist) {
     double tn[3] = {0, 0, 0};
     double last_s = NAN;
     auto phi = [&](double sv, int& err) -> double {
-      err = eval_residual(x, sol, sref(-sv), xt, Ft, Gt, JS_F2_B, tn);
+      if (trial_.valid && sv == 1.0) { // F(x - dx) came with the cycle's launch
+        trial_.valid = false;
+        for (int i = 0; i < 3; ++i) tn[i] = trial_.nrm[i];
+        nfev_++;
+        err = ops_->status();
+      } else {
+        trial_.valid = false;
+        err = eval_residual(x, sol, sref(-sv), xt, Ft, Gt, JS_F2_B, tn);
+      }
       last_s = sv;
       if (!isfinite(tn[0])) return inf; // _safe_norm
       double nv = sqrt(tn[0]);

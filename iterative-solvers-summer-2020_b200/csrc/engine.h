@@ -120,6 +120,14 @@ class Engine {
   double omega_ = 0.0;
   bool linear_op_ = false; // true: SH_LINEAR operator instead of the FD Jacobian
 
+  // The first line-search trial F(x - dx) of a Newton iteration, evaluated by the launch that ran the inner cycle
+  // (DeviceOps::cycle_fused): newton() says where it wants it before calling cycle(), cycle() reports whether it was done.
+  struct Trial {
+    bool want = false, valid = false;
+    double *xt = nullptr, *Ft = nullptr, *Gt = nullptr;
+    double nrm[3] = {0, 0, 0};
+  } trial_;
+
   // statistics of the running solve
   int64_t nfev_ = 0, inner_total_ = 0, reorth_total_ = 0;
 };

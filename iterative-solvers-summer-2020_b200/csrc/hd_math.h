@@ -72,10 +72,16 @@ JF_HD double shlin_apply(const SHParams& p, double z, double Lz, double D) { ret
 // S = scalar arena.  j = Arnoldi index (column), so the column has j+2 entries.
 // taken != 0: a second Gram-Schmidt pass was made (RD2, HN2B valid).  rerun != 0: the step for this j already ran
 // once after the first pass (the host then decided to re-orthogonalise): restart from the saved rotated rhs.
-JF_HD void hess_givens_step(double* S, int j, int taken, int rerun) {
+// h_i = (V_i . w)/||V_i|| with V_i stored unnormalised (first-pass dots plus the second pass's when one was taken)
+JF_HD double hess_entry(const double* S, int i, int taken) {
+  double h = S[JS_RD + i];
+  if (taken) h += S[JS_RD2 + i];
+  return h / sqrt(S[JS_VN2 + i]);
+}
+// hpre: the column entries h_0..h_j already evaluated with hess_entry (a kernel whose threads do that in parallel), or null
+JF_HD void hess_givens_step(double* S, int j, int taken, int rerun, const double* hpre = nullptr) {
   const double eps = 2.220446049250313e-16;
   double* rd = S + JS_RD;
-  double* rd2 = S + JS_RD2;
   double* vn2 = S + JS_VN2;
   double* cs = S + JS_CS;
   double* sn = S + JS_SN;
@@ -89,12 +95,9 @@ JF_HD void hess_givens_step(double* S, int j, int taken, int rerun) {
   if (j == 0) g[0] = 1.0;
   if (rerun) g[j] = S[JS_GJ_SAVE];
   else S[JS_GJ_SAVE] = g[j];
-  // h_i = (V_i . w)/||V_i|| with V_i stored unnormalised
   double hprev = 0.0;
   for (int i = 0; i <= j; ++i) {
-    double h = rd[i];
-    if (taken) h += rd2[i];
-    h /= sqrt(vn2[i]);
+    double h = hpre ? hpre[i] : hess_entry(S, i, taken);
     if (i > 0) {
       // apply rotation i-1 to (hprev, h)
       double t = cs[i - 1] * hprev + sn[i - 1] * h;

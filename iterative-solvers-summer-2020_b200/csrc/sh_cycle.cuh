@@ -42,11 +42,18 @@ struct CycleArgs {
   double* out;       // dx
   int out_zn2;       // arena index of ||dx||^2
   double* S;         // the context's scalar arena (global memory)
+  // optional: the first line-search trial of the Newton step that follows (nonlin_solve's phi(1), _nonlin.py:300-305)
+  // evaluated in the same launch -- t = x0 - dx, F = G(t) - d, G(t), and the three norms at S[trial_norm_off..+2]
+  const double* d;   // per-step constant field (null: no trial)
+  double *trial_x, *trial_F, *trial_G;
+  int trial_norm_off;
+  long long* prof;   // optional (JFNK_CYCLE_PROF=1): clock cycles per phase, accumulated by CTA 0
 };
+enum CyclePhase { CP_LOAD = 0, CP_BUILD, CP_APPLY, CP_DOTS, CP_UPDATE, CP_GIVENS, CP_ASSEMBLE, CP_TRIAL, CP_TOTAL, CP_STEPS, CP_CYCLES, CP_COUNT };
 
 // shared-memory layout (doubles); identical in every CTA so that map_shared_rank() addresses match
 struct CycleLayout {
-  int arena, mailD, mailN, mailX, cf, x0e, g0, t, v;
+  int arena, mailD, mailN, mailX, cf, idx, x0e, g0, t, v;
   size_t total;
   __host__ __device__ CycleLayout(int pitch, int ext, int m) {
     int o = 0;
@@ -55,6 +62,7 @@ struct CycleLayout {
     mailN = o; o += kCycMaxCluster * 8;
     mailX = o; o += kCycMaxCluster * 8;
     cf = o; o += JF_MAXV;
+    idx = o; o += ((ext + 1) / 2) * 2 + (pitch + 1) / 2; // int tables: 2 per extended-band point, 1 per band point
     x0e = o; o += ext;
     g0 = o; o += pitch;
     t = o; o += ext;
@@ -75,6 +83,7 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
   extern __shared__ __align__(16) double cyc_smem[];
   __shared__ int r0tab[kCycMaxCluster + 1];
   __shared__ int znidx[JF_MAXV];
+  __shared__ double hpre[JF_MAXV + 1];
   const CycleLayout L(A.pitch, A.ext, A.m);
   double* Ssm = cyc_smem + L.arena;
   double* mailD = cyc_smem + L.mailD; // [src CTA][kCycMailW]
@@ -86,20 +95,37 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
   double* T = cyc_smem + L.t;
   double* V = cyc_smem + L.v;
   const int nx = A.nx, ny = A.ny, k = A.k, m = A.m;
-  if (tid <= C) r0tab[tid] = (int)(((long long)tid * ny) / C);
+  const bool timing = (A.prof != nullptr) && me == 0 && tid == 0;
+  long long tlast = timing ? clock64() : 0;
+  const long long tstart = tlast;
+  auto tick = [&](int phase) {
+    if (timing) { const long long t = clock64(); A.prof[phase] += t - tlast; tlast = t; }
+  };
+  if (tid <= C) r0tab[tid] = (tid * ny) / C;
   __syncthreads();
   const int r0 = r0tab[me], rows = r0tab[me + 1] - r0;
   const int Pn = rows * nx, En = (rows + 4) * nx;
   const size_t g0off = (size_t)r0 * nx;
+  // index tables, fixed for the whole cycle: for every point of the extended band its global offset and where its value
+  // lives in the cluster (owner CTA << 20 | offset inside the owner's band); for every band point its column
+  int* egoff = reinterpret_cast<int*>(cyc_smem + L.idx);
+  int* esrc = egoff + ((A.ext + 1) / 2) * 2;
+  int* pcol = esrc + ((A.ext + 1) / 2) * 2;
+  for (int e = tid; e < En; e += kCycThreads) {
+    const int rg = cyc_mod(r0 - 2 + e / nx, ny), c = e % nx;
+    int o = (rg * C) / ny;
+    while (r0tab[o + 1] <= rg) ++o;
+    while (r0tab[o] > rg) --o;
+    egoff[e] = rg * nx + c;
+    esrc[e] = (o << 20) | ((rg - r0tab[o]) * nx + c);
+  }
+  for (int p = tid; p < Pn; p += kCycThreads) pcol[p] = p % nx;
 
   // ---- load: scalar arena, linearisation point with halos, G(x0) / D, start vector -----------------------------------
-  for (int i = tid; i < JS_COUNT; i += kCycThreads) Ssm[i] = A.S[i];
-  for (int e = tid; e < En; e += kCycThreads) {
-    if (OP == OP_JVPG) {
-      const int rg = cyc_mod(r0 - 2 + e / nx, ny);
-      X0e[e] = A.x0[(size_t)rg * nx + (e % nx)];
-    }
-  }
+  // (everything the cycle reads from the arena it has written itself, except the norms of the augmentation vectors)
+  for (int i = tid; i < JS_COUNT; i += kCycThreads) Ssm[i] = (i >= JS_ZN2 && i < JS_ZN2 + JF_MAXOV) ? A.S[i] : 0.0;
+  if (OP == OP_JVPG)
+    for (int e = tid; e < En; e += kCycThreads) X0e[e] = A.x0[egoff[e]];
   for (int p = tid; p < Pn; p += kCycThreads) {
     G0[p] = A.g0[g0off + p];
     V[p] = A.v0[g0off + p];
@@ -112,19 +138,17 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
     Ssm[JS_TAU2] = (A.gs_mode == JFNK_GS_CGS_IFNEEDED) ? A.tau2 : 0.0;
   }
   cl.sync(); // every CTA's band of v0 is in place before a neighbour reads its halo rows
+  tick(CP_LOAD);
 
   // the band of z rows [r0-2, r0+rows+2) as operator input: T = x0 + sc z (FD Jacobian) or z (linear operator)
   auto build_T = [&](const double* zglobal, const double* zband, double sc) {
     for (int e = tid; e < En; e += kCycThreads) {
-      const int rg = cyc_mod(r0 - 2 + e / nx, ny), c = e % nx;
       double zv;
-      if (zglobal) zv = zglobal[(size_t)rg * nx + c];
+      if (zglobal) zv = zglobal[egoff[e]];
       else {
-        int o = (int)(((long long)rg * C) / ny);
-        while (r0tab[o + 1] <= rg) ++o;
-        while (r0tab[o] > rg) --o;
+        const int o = esrc[e] >> 20;
         const double* src = (o == me) ? zband : cl.map_shared_rank(zband, o);
-        zv = src[(rg - r0tab[o]) * nx + c];
+        zv = src[esrc[e] & 0xfffff];
       }
       T[e] = (OP == OP_JVPG) ? combine(X0e[e], sc, zv) : zv;
     }
@@ -133,10 +157,10 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
   auto apply = [&](double* W, double scale) {
     ShAcc acc = {0.0, 0.0, 0.0};
     for (int p = tid; p < Pn; p += kCycThreads) {
-      const int r = p / nx, c = p - r * nx;
+      const int c = pcol[p];
       const int cm1 = c - 1 < 0 ? c - 1 + nx : c - 1, cm2 = c - 2 < 0 ? c - 2 + nx : c - 2;
       const int cp1 = c + 1 >= nx ? c + 1 - nx : c + 1, cp2 = c + 2 >= nx ? c + 2 - nx : c + 2;
-      const double* t0 = T + (r + 2) * nx; // row r of the band
+      const double* t0 = T + (p - c) + 2 * nx; // the point's row inside the extended band
       const double uc = t0[c];
       const double a1 = t0[cm1] + t0[cp1];
       const double a2 = t0[cm2] + t0[cp2];
@@ -149,24 +173,40 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
       W[p] = sh_value<OP>(P, scale, uc, s1, sd, s2, G0[p], 0.0, second, third, acc);
     }
   };
-  // all-reduced dots of V_0..V_{nd-1} with W into Ssm[off + i] (every CTA sums the same partials in the same order)
+  // all-reduced dots of V_0..V_{nd-1} with W into Ssm[off + i] (every CTA sums the same partials in the same order).
+  // Warp w takes the vectors w, w + 8, ...: up to 6 independent accumulators and interleaved shuffle reductions per warp.
   auto dots = [&](int nd, const double* W, int off) {
-    for (int i = warp; i < nd; i += NW) {
-      const double* vi = V + (size_t)i * A.pitch;
-      double s = 0.0;
-      for (int p = lane; p < Pn; p += 32) s = fma(vi[p], W[p], s);
-      s = warp_sum(s);
-      if (lane < C) {
-        double* dst = (lane == me) ? mailD : cl.map_shared_rank(mailD, lane);
-        dst[me * kCycMailW + i] = s;
-      }
+    constexpr int Q = (JF_MAXV + NW - 1) / NW;
+    double s[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) s[q] = 0.0;
+    const int nq = (nd - warp + NW - 1) / NW; // vectors of this warp
+    const double* v0p = V + (size_t)warp * A.pitch;
+    for (int p = lane; p < Pn; p += 32) {
+      const double wv = W[p];
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        if (q < nq) s[q] = fma(v0p[(size_t)q * NW * A.pitch + p], wv, s[q]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+    if (lane < C) {
+      double* dst = ((lane == me) ? mailD : cl.map_shared_rank(mailD, lane)) + me * kCycMailW + warp;
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        if (q < nq) dst[q * NW] = s[q];
     }
     cl.sync();
     if (tid < nd) {
-      double s = 0.0;
-      for (int o = 0; o < C; ++o) s += mailD[o * kCycMailW + tid];
-      Ssm[off + tid] = s;
-      if (tid < nd - 1) cf[tid] = -(s / Ssm[JS_VN2 + tid]); // Gram-Schmidt coefficient of the unnormalised V_i
+      double t = 0.0;
+      for (int o = 0; o < C; ++o) t += mailD[o * kCycMailW + tid];
+      Ssm[off + tid] = t;
+      if (tid < nd - 1) {
+        cf[tid] = -(t / Ssm[JS_VN2 + tid]);                 // Gram-Schmidt coefficient of the unnormalised V_i
+        hpre[tid] = hess_entry(Ssm, tid, off == JS_RD2);    // Hessenberg column entry, all rows in parallel
+      }
     }
     __syncthreads();
   };
@@ -213,11 +253,15 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
     double* W = V + (size_t)(j + 1) * A.pitch;
     build_T(zg, zb, A.omega / zn);
     __syncthreads();
+    tick(CP_BUILD);
     apply(W, OP == OP_JVPG ? 1.0 / A.omega : 1.0 / zn);
     __syncthreads();
+    tick(CP_APPLY);
     // classical Gram-Schmidt against V_0..V_j: all dots (and w.w) in one exchange, the update and its norm in another
     dots(j + 2, W, JS_RD);
+    tick(CP_DOTS);
     double hn2 = update(j + 1, W);
+    tick(CP_UPDATE);
     int taken = 0;
     if (A.gs_mode == JFNK_GS_CGS2) {
       if (tid == 0) Ssm[JS_HN2A] = hn2;
@@ -226,27 +270,48 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
       if (tid == 0) Ssm[JS_HN2B] = hn2;
       taken = 1;
     } else if (tid == 0) Ssm[JS_HN2A] = hn2;
-    if (tid == 0) hess_givens_step(Ssm, j, taken, 0);
+    if (tid == 0) hess_givens_step(Ssm, j, taken, 0, hpre);
     __syncthreads();
     flags = (int)Ssm[JS_FLAGS];
     if (flags & JF_FLAG_NEED_REORTH) {
       // the first pass cancelled more than 1/tau: second pass, then column j again from the saved rotated rhs
       dots(j + 2, W, JS_RD2);
       hn2 = update(j + 1, W);
-      if (tid == 0) { Ssm[JS_HN2B] = hn2; hess_givens_step(Ssm, j, 1, 1); }
+      if (tid == 0) { Ssm[JS_HN2B] = hn2; hess_givens_step(Ssm, j, 1, 1, hpre); }
       __syncthreads();
       flags = (int)Ssm[JS_FLAGS];
       taken = 1;
     }
+    tick(CP_GIVENS);
     if (taken) ++reorth;
     res = Ssm[JS_RES];
     nit = j + 1;
     if ((flags & (JF_FLAG_BREAKDOWN | JF_FLAG_NONFINITE)) || res < A.ptol) break;
   }
 
-  // y = lstsq(R, Q[0,:]) * ||v0|| ; dx = sum y_i z_i (lgmres.py:188,206-208)
-  if (tid == 0) lsq_solve(Ssm, nit, znidx, JS_VN2 + 0);
+  // y = lstsq(R, Q[0,:]) * ||v0|| ; dx = sum y_i z_i (lgmres.py:188,206-208).  Back-substitution by warp 0, one column
+  // per step (lane r owns rows r and r + 32); a zero pivot (Arnoldi breakdown) yields y_i = 0 like lsq_solve (hd_math.h).
+  if (warp == 0) {
+    const double* R = Ssm + JS_R;
+    double a0 = (lane < nit) ? Ssm[JS_G + lane] : 0.0;
+    double a1 = (lane + 32 < nit) ? Ssm[JS_G + lane + 32] : 0.0;
+    for (int i = nit - 1; i >= 0; --i) {
+      const double piv = R[i + (size_t)i * JF_MAXV];
+      const double ai = __shfl_sync(0xffffffffu, (i < 32) ? a0 : a1, i & 31);
+      const double yi = (piv != 0.0) ? ai / piv : 0.0;
+      if (lane == 0) Ssm[JS_Y + i] = yi;
+      if (lane < i) a0 = fma(-R[lane + (size_t)i * JF_MAXV], yi, a0);
+      if (lane + 32 < i) a1 = fma(-R[lane + 32 + (size_t)i * JF_MAXV], yi, a1);
+    }
+  }
   __syncthreads();
+  if (tid < nit) {
+    const double y = Ssm[JS_Y + tid] * sqrt(Ssm[JS_VN2 + 0]);
+    Ssm[JS_Y + tid] = y;
+    Ssm[JS_COEF + tid] = y / sqrt(Ssm[znidx[tid]]);
+  }
+  __syncthreads();
+  double* DX = V + (size_t)m * A.pitch; // the slot of the last possible Arnoldi vector: never an input of the assembly
   double acc = 0.0;
   for (int p = tid; p < Pn; p += kCycThreads) {
     double t = 0.0;
@@ -255,19 +320,69 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
       t = fma(Ssm[JS_COEF + i], zv, t);
     }
     A.out[g0off + p] = t;
+    DX[p] = t;
     acc = fma(t, t, acc);
   }
-  const double dxn2 = allsum(acc, mailX);
+  const double dxn2 = allsum(acc, mailX); // (its cluster barrier also publishes the DX bands)
+  tick(CP_ASSEMBLE);
+  double tn[3] = {0.0, 0.0, 0.0};
+  if (OP == OP_JVPG && A.d != nullptr) {
+    // F(x0 - dx): the operand band with halos, the residual with its norms, all-reduced like the dots
+    build_T(nullptr, DX, -1.0);
+    __syncthreads();
+    ShAcc ra = {0.0, 0.0, 0.0};
+    for (int p = tid; p < Pn; p += kCycThreads) {
+      const int c = pcol[p];
+      const int cm1 = c - 1 < 0 ? c - 1 + nx : c - 1, cm2 = c - 2 < 0 ? c - 2 + nx : c - 2;
+      const int cp1 = c + 1 >= nx ? c + 1 - nx : c + 1, cp2 = c + 2 >= nx ? c + 2 - nx : c + 2;
+      const double* t0 = T + (p - c) + 2 * nx;
+      const double uc = t0[c];
+      const double a1 = t0[cm1] + t0[cp1];
+      const double a2 = t0[cm2] + t0[cp2];
+      const double a1u = t0[cm1 - nx] + t0[cp1 - nx];
+      const double a1d = t0[cm1 + nx] + t0[cp1 + nx];
+      const double s1 = a1 + t0[c - nx] + t0[c + nx];
+      const double sd = a1u + a1d;
+      const double s2 = a2 + t0[c - 2 * nx] + t0[c + 2 * nx];
+      double second = 0.0, third = 0.0;
+      const double F = sh_value<OP_RESID>(P, 1.0, uc, s1, sd, s2, A.d[g0off + p], 0.0, second, third, ra);
+      A.trial_F[g0off + p] = F;
+      A.trial_x[g0off + p] = second;
+      A.trial_G[g0off + p] = third;
+    }
+    // sum F^2 (sum), max|F|, max|t| (max): per-warp partials to every CTA's mailbox, every CTA reduces all of them
+    const double f2w = warp_sum(ra.f2), fmw = warp_max(ra.fmax), xmw = warp_max(ra.xmax);
+    if (lane < C) {
+      double* dst = ((lane == me) ? mailD : cl.map_shared_rank(mailD, lane)) + me * kCycMailW + warp * 3;
+      dst[0] = f2w; dst[1] = fmw; dst[2] = xmw;
+    }
+    cl.sync();
+    if (warp == 0) {
+      double f2 = 0.0, fm = 0.0, xm = 0.0;
+      for (int q = lane; q < C * NW; q += 32) {
+        const double* src = mailD + (q / NW) * kCycMailW + (q % NW) * 3;
+        f2 += src[0]; fm = fmax(fm, src[1]); xm = fmax(xm, src[2]);
+      }
+      tn[0] = warp_sum(f2); tn[1] = warp_max(fm); tn[2] = warp_max(xm);
+    }
+    tick(CP_TRIAL);
+  }
   if (me == 0) {
     if (tid == 0) {
       Ssm[A.out_zn2] = dxn2;
       Ssm[JS_STOP] = 0.0;
       double* cyc = Ssm + JS_CYC;
       cyc[0] = (double)nit; cyc[1] = (double)reorth; cyc[2] = res; cyc[3] = (double)flags; cyc[4] = dxn2;
+      cyc[5] = tn[0]; cyc[6] = tn[1]; cyc[7] = tn[2];
+      if (OP == OP_JVPG && A.d != nullptr) { A.S[A.trial_norm_off] = tn[0]; A.S[A.trial_norm_off + 1] = tn[1]; A.S[A.trial_norm_off + 2] = tn[2]; }
     }
     __syncthreads();
-    for (int i = JS_WW + tid; i < JS_COUNT; i += kCycThreads) A.S[i] = Ssm[i];
+    // back to the arena: everything but the triangular factor (no later kernel or host code reads it)
+    for (int i = JS_WW + tid; i < JS_R; i += kCycThreads) A.S[i] = Ssm[i];
+    for (int i = JS_STOP + tid; i < JS_COUNT; i += kCycThreads) A.S[i] = Ssm[i];
   }
+  tick(CP_ASSEMBLE);
+  if (timing) { A.prof[CP_TOTAL] += clock64() - tstart; A.prof[CP_STEPS] += nit; A.prof[CP_CYCLES] += 1; }
 }
 
 } // namespace jfnk
