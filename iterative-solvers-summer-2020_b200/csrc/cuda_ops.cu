@@ -31,10 +31,11 @@ inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 // kernel classes of the per-kernel timing (bench.py roofline); bytes are the ALGORITHMIC bytes of DESIGN.md
 enum KClass { K_MDOT = 0, K_GS_UPDATE, K_MAXPY, K_LINCOMB, K_SPMV_LAP, K_SPMV_L, K_SET_PREV, K_RESIDUAL, K_JVP,
-              K_SHLIN, K_MESH, K_SCALAR, K_MDOT2, K_GS_UPDATE2, K_HALO, K_ALLREDUCE, K_CYCLE, K_COUNT };
+              K_SHLIN, K_MESH, K_SCALAR, K_MDOT2, K_GS_UPDATE2, K_HALO, K_ALLREDUCE, K_CYCLE, K_MESH_LAP, K_MESH_FLUX, K_MESH_DIV, K_COUNT };
 const char* const kClassName[K_COUNT] = {"mdot", "gs_update", "maxpy", "lincomb", "spmv_lap", "spmv_L", "set_prev",
                                          "sh_residual", "sh_jvp", "shlin", "mesh", "scalar", "mdot_pass2",
-                                         "gs_update_pass2", "halo_exchange", "allreduce", "lgmres_cycle"};
+                                         "gs_update_pass2", "halo_exchange", "allreduce", "lgmres_cycle", "mesh_lap", "mesh_flux",
+                                         "mesh_div"};
 
 class CudaOps : public DeviceOps {
  public:
@@ -209,6 +210,7 @@ class CudaOps : public DeviceOps {
     const char* e = getenv("JFNK_SPECULATE"); // (read per cycle: the parity tests flip it)
     return !(e && atoi(e) == 0) && (g_.nranks == 1 || p2p_);
   }
+  bool can_speculate_mesh() const override { return true; }
   void post_read(int slot, int off, int cnt) override {
     if (!ck(cudaMemcpyAsync(posted_pin_ + 8 * slot, S_ + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, stream_), "D2H record")) return;
     ck(cudaEventRecord(posted_ev_[slot], stream_), "cudaEventRecord");
@@ -813,16 +815,32 @@ class CudaOps : public DeviceOps {
                  ScalarRef a, const double* uval, const double* cn, const double* f0, ScalarRef div,
                  double* const* scratch, double* xt_out, double* out, int norm_off) override {
     if (!use_march()) {
-      pma2_eval_unfused(mp, pp, M, x, v, a, uval, cn, f0, div, scratch, xt_out, out, norm_off);
+      // reference-sized grids: two launches (mesh_kernels.cuh), t = x + a v formed on the fly
+      MeshGeom gm = geom(mp);
+      const int skip = f0 ? 1 : 0;
+      double* tt = v ? ((xt_out && !f0) ? xt_out : scratch[3]) : nullptr;
+      const double* u = v ? tt : x;
+      DropletParams nodp;
+      memset(&nodp, 0, sizeof(nodp));
+      {
+        Prof prof(this, K_MESH, nb(6.0 + (v ? 2.0 : 0.0)));
+        if (v) mesh_lap_fused_kernel<0, true><<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), x, v, a, nodp, tt, scratch[0], S_, skip);
+        else mesh_lap_fused_kernel<0, false><<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), x, v, a, nodp, tt, scratch[0], S_, skip);
+      }
+      Prof prof(this, K_MESH, nb(9.0 + (f0 ? 1.0 : 0.0)));
+      if (f0) pma2_lap_fused_kernel<true><<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), pp, scratch[0], u, uval, cn, f0, div, out, S_, norm_off, ws_, skip);
+      else pma2_lap_fused_kernel<false><<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), pp, scratch[0], u, uval, cn, f0, div, out, S_, norm_off, ws_, skip);
       return;
     }
     // pass 1: lap1 = Laplace(x + a v) (+ the trial iterate when the caller keeps it)
     MarchArgs A = march_args(M, x, v, a, scratch[0]);
     A.out2 = (v && !f0) ? xt_out : nullptr;
+    A.skippable = f0 ? 1 : 0;
     if (v) march_launch<MARCH_LAP, true>(A, mp, 7.0 + (A.out2 ? 1.0 : 0.0));
     else march_launch<MARCH_LAP, false>(A, mp, 6.0);
     // pass 2: Laplace(lap1) with the pointwise PMA2 terms, the Crank-Nicolson combination and the FD quotient fused in
     MarchArgs B = march_args(M, scratch[0], nullptr, sref(0.0), out);
+    B.skippable = f0 ? 1 : 0;
     B.px = x; B.pv = v; B.pa = a; B.uval = uval; B.cn = cn; B.f0 = f0; B.div = div; B.pp = pp; B.norm_off = norm_off;
     const double vecs = 9.0 + (v ? 1.0 : 0.0) + (f0 ? 1.0 : 0.0); // lap1, 4 metric fields, x, (v), uval, cn, (f0); out
     if (f0) march_launch<MARCH_PMA2_JVP, false>(B, mp, vecs);
@@ -859,7 +877,28 @@ class CudaOps : public DeviceOps {
                     const double* h, double* A, double* B) override {
     MeshGeom gm = geom(mp);
     Prof prof(this, K_MESH, nb(8));
-    droplet_flux_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, dp, cptrs(M), p, h, A, B);
+    droplet_flux_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, dp, cptrs(M), p, h, A, B, S_, 0);
+  }
+  // the droplet residual / FD-JVP chain in three launches (mesh_kernels.cuh)
+  void droplet_eval(const MeshParams& mp, const DropletParams& dp, const double* const* M, const double* x, const double* v,
+                    ScalarRef a, const double* uval, const double* fprev, const double* f0, ScalarRef div,
+                    double* const* scratch, double* xt_out, double* out, int norm_off) override {
+    MeshGeom gm = geom(mp);
+    const int skip = f0 ? 1 : 0;
+    double* tt = v ? ((xt_out && !f0) ? xt_out : scratch[5]) : nullptr;
+    const double* u = v ? tt : x;
+    {
+      Prof prof(this, K_MESH_LAP, nb(6.0 + (v ? 2.0 : 0.0)));
+      if (v) mesh_lap_fused_kernel<1, true><<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), x, v, a, dp, tt, scratch[1], S_, skip);
+      else mesh_lap_fused_kernel<1, false><<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), x, v, a, dp, tt, scratch[1], S_, skip);
+    }
+    {
+      Prof prof(this, K_MESH_FLUX, nb(8));
+      droplet_flux_kernel<<<tile_grid(), 256, 0, stream_>>>(gm, dp, cptrs(M), scratch[1], u, scratch[2], scratch[3], S_, skip);
+    }
+    Prof prof(this, K_MESH_DIV, nb(10.0 + (f0 ? 1.0 : 0.0)));
+    if (f0) droplet_div_fused_kernel<true><<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), dp, scratch[2], scratch[3], u, uval, fprev, f0, div, out, S_, norm_off, ws_, skip);
+    else droplet_div_fused_kernel<false><<<tile_grid(), 256, 0, stream_>>>(gm, cptrs(M), dp, scratch[2], scratch[3], u, uval, fprev, f0, div, out, S_, norm_off, ws_, skip);
   }
   void droplet_div(const MeshParams& mp, const double* const* M, const double* A, const double* B, double* out) override {
     MeshGeom gm = geom(mp);

@@ -124,6 +124,8 @@ class DeviceOps {
   // true: the operator / multi-dot / update kernels of this backend return at once while S[JS_STOP] is set, so the
   // engine may enqueue Arnoldi step j+1 before it has seen the outcome of step j (Engine::cycle)
   virtual bool can_speculate() const { return false; }
+  // ... and so do the kernels behind pma2_eval / droplet_eval in operator mode (f0 != null)
+  virtual bool can_speculate_mesh() const { return false; }
   // enqueue a copy of S[off..off+cnt) into host slot `slot` (0 <= slot < JF_MAXV + 1, cnt <= 8) ...
   virtual void post_read(int slot, int off, int cnt) { read_scalars(off, cnt, posted_[slot]); }
   // ... and wait for exactly that copy (later work may still be running on the device)
@@ -227,6 +229,31 @@ class DeviceOps {
       diff_scale(out, scratch[0], f0, div);
     } else {
       pma2_combine(pp, t, uval, scratch[2], cn, out, norm_off);
+    }
+  }
+  // Whole droplet residual / FD-JVP (droplet.py:435-450) for t = x + a v (v may be null):
+  //   F = (t - uval) - dt (div(flux(p(t, Laplace(t)), t)) + fprev)/2
+  //   f0 == null: out = F, xt_out (may be null) = t when v is given, norms at S[norm_off..+2] as sh_residual
+  //   f0 != null: out = (F - f0)/div                                   (KrylovJacobian.matvec)
+  // scratch: 7 work vectors.  The CUDA backend fuses the chain into three launches; the default composes the primitives.
+  virtual void droplet_eval(const MeshParams& mp, const DropletParams& dp, const double* const* M, const double* x,
+                            const double* v, ScalarRef a, const double* uval, const double* fprev, const double* f0,
+                            ScalarRef div, double* const* scratch, double* xt_out, double* out, int norm_off) {
+    const double* t = x;
+    if (v) {
+      double* tt = (xt_out && !f0) ? xt_out : scratch[5];
+      lincomb(tt, sref(1.0), x, a, v, -1);
+      t = tt;
+    }
+    mesh_laplace(mp, M, t, scratch[0], nullptr, 1, 0);
+    droplet_pressure(dp, t, scratch[0], scratch[1]);
+    droplet_flux(mp, dp, M, scratch[1], t, scratch[2], scratch[3]);
+    droplet_div(mp, M, scratch[2], scratch[3], scratch[4]);
+    if (f0) {
+      droplet_combine(dp, t, uval, scratch[4], fprev, scratch[6], norm_off);
+      diff_scale(out, scratch[6], f0, div);
+    } else {
+      droplet_combine(dp, t, uval, scratch[4], fprev, out, norm_off);
     }
   }
   // droplet: p = -(lap) + PI(h) + Bo cos(alpha2) h

@@ -310,11 +310,8 @@ void Engine::generic_residual(const double* u, double* F, int norm_off) {
                     norm_off);
   } else {
     // droplet.py:435-450
-    ops_->mesh_laplace(mp_, MF_, u, scratch_[0], nullptr, 1, 0);
-    ops_->droplet_pressure(dp_, u, scratch_[0], scratch_[1]);
-    ops_->droplet_flux(mp_, dp_, MF_, scratch_[1], u, scratch_[2], scratch_[3]);
-    ops_->droplet_div(mp_, MF_, scratch_[2], scratch_[3], scratch_[4]);
-    ops_->droplet_combine(dp_, u, UVAL_, scratch_[4], CN_, F, norm_off);
+    ops_->droplet_eval(mp_, dp_, MF_, u, nullptr, sref(1.0), UVAL_, CN_, nullptr, sref(1.0), scratch_.data(), nullptr, F,
+                       norm_off);
   }
 }
 
@@ -328,15 +325,9 @@ int Engine::eval_residual(const double* x, const double* v, ScalarRef a, double*
     ops_->pma2_eval(mp_, pp_, MF_, x, v, a, UVAL_, CN_, nullptr, sref(1.0), scratch_.data(), v ? xt_out : nullptr, F,
                     norm_off);
   } else {
-    const double* t = x;
-    if (v) {
-      double* tt = xt_out ? xt_out : scratch_[5];
-      ops_->lincomb(tt, sref(1.0), x, a, v, -1);
-      t = tt;
-    } else if (xt_out && xt_out != x) {
-      ops_->copy(xt_out, x);
-    }
-    generic_residual(t, F, norm_off);
+    if (!v && xt_out && xt_out != x) ops_->copy(xt_out, x);
+    ops_->droplet_eval(mp_, dp_, MF_, x, v, a, UVAL_, CN_, nullptr, sref(1.0), scratch_.data(), v ? xt_out : nullptr, F,
+                       norm_off);
   }
   ops_->allreduce_sum(norm_off, 1);
   ops_->allreduce_max(norm_off + 1, 2);
@@ -383,9 +374,7 @@ void Engine::apply_operator(const double* z, int zn2_idx, double* w, bool unit_i
   } else if (cfg_.problem == JFNK_PROBLEM_PMA2) {
     ops_->pma2_eval(mp_, pp_, MF_, x0_, z, sc, UVAL_, CN_, f0_, div, scratch_.data(), nullptr, w, JS_TMP0 /*unused*/);
   } else {
-    ops_->lincomb(scratch_[5], sref(1.0), x0_, sc, z, -1);
-    generic_residual(scratch_[5], scratch_[6], JS_TMP0 /*norms unused*/);
-    ops_->diff_scale(w, scratch_[6], f0_, div);
+    ops_->droplet_eval(mp_, dp_, MF_, x0_, z, sc, UVAL_, CN_, f0_, div, scratch_.data(), nullptr, w, JS_TMP0 /*unused*/);
   }
   nfev_++;
 }
@@ -481,7 +470,7 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
   // step j's record, and the kernels of a step enqueued after the stop return at once.  The stream never drains inside
   // the loop and nothing that was not needed runs.  Needs kernels that honour JS_STOP (DeviceOps::can_speculate; the
   // multi-kernel mesh residuals and preconditioner callbacks do not).
-  const bool spec = ops_->can_speculate() && !psolve_ && !is_mesh_problem(cfg_.problem);
+  const bool spec = ops_->can_speculate() && !psolve_ && (!is_mesh_problem(cfg_.problem) || ops_->can_speculate_mesh());
   {
     const double ctl[3] = {0.0, spec ? ptol : -1.0, (spec && cfg_.gs_mode == JFNK_GS_CGS_IFNEEDED) ? tau2 : 0.0};
     ops_->write_scalars(JS_STOP, 3, ctl); // JS_STOP, JS_PTOL, JS_TAU2

@@ -79,12 +79,14 @@ struct MarchArgs {
   double *out, *out2;
   int norm_off, deriv_bc;
   int rows_per_chunk, nstrips, nframe_ctas;
+  int skippable;  // part of a speculatively enqueued Arnoldi step: return at once while JS_STOP is set
   int debug_skip; // profiling aid (JFNK_MARCH_DEBUG): 1 = frame CTAs idle, 2 = interior CTAs idle; results are then wrong
 };
 
 template <int MODE, bool HAS_V>
 __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_kernel(const __grid_constant__ MarchArgs A, double* S,
                                                                        ReduceWs ws) {
+  if (A.skippable && S[JS_STOP] != 0.0) return;
   constexpr int W = kMarchW;
   constexpr int NF = march_fields(MODE);
   extern __shared__ __align__(16) unsigned char march_smem[];
