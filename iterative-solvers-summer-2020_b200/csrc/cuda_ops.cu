@@ -17,6 +17,7 @@
 #include "mesh_march.cuh"
 #include "pma_kernels.cuh"
 #include "pma_relax.cuh"
+#include "pma_relax_band.cuh"
 #include "nccl_dl.h"
 #include "p2p_kernels.cuh"
 #include "sh_kernels.cuh"
@@ -955,7 +956,7 @@ class CudaOps : public DeviceOps {
                         int deriv_bc, double* const* M, double* a, double* b, double* t, double* spec) override {
     static const bool off = getenv("JFNK_RELAX_FUSED") && atoi(getenv("JFNK_RELAX_FUSED")) == 0;
     const size_t smem = sizeof(double) * ((size_t)g_.nx * g_.nx + (size_t)g_.ny * g_.ny + g_.n());
-    if (off || capturing_ || smem > (size_t)200 * 1024 || loops < 1) return false;
+    if (off || capturing_ || loops < 1) return false;
     if (!ensure_dct()) return false;
     RelaxArgs A;
     memset(&A, 0, sizeof(A));
@@ -966,6 +967,41 @@ class CudaOps : public DeviceOps {
     A.a = a; A.b = b; A.t = t; A.spec = spec;
     A.dctx = dctx_; A.dcty = dcty_;
     A.partials = ws_.partials;
+    // second generation (pma_relax_band.cuh): every field resident in the cluster's shared memory, five barriers per pass
+    static const bool band_off = getenv("JFNK_RELAX_BAND") && atoi(getenv("JFNK_RELAX_BAND")) == 0;
+    if (!band_off && pp.smoothing_iters <= 4 && g_.ny >= 8 && g_.nx >= 16) {
+      if (band_cluster_ == 0) {
+        band_cluster_ = -1;
+        cudaFuncSetAttribute(pma_relax_band_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        for (int cs : {16, 8}) {
+          if (g_.ny < cs || g_.nx < cs) continue;
+          const size_t need = BandLayout(g_.nx, g_.ny, cs).total;
+          if (need > (size_t)226 * 1024) continue;
+          if (cudaFuncSetAttribute(pma_relax_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) continue;
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kBandThreads); cfg.dynamicSmemBytes = need;
+          cudaLaunchAttribute at;
+          at.id = cudaLaunchAttributeClusterDimension;
+          at.val.clusterDim.x = cs; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+          cfg.attrs = &at; cfg.numAttrs = 1;
+          int nclusters = 0;
+          if (cudaOccupancyMaxActiveClusters(&nclusters, pma_relax_band_kernel, &cfg) == cudaSuccess && nclusters >= 1) { band_cluster_ = cs; break; }
+        }
+        cudaGetLastError();
+      }
+      if (band_cluster_ > 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(band_cluster_); cfg.blockDim = dim3(kBandThreads);
+        cfg.dynamicSmemBytes = BandLayout(g_.nx, g_.ny, band_cluster_).total; cfg.stream = stream_;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = band_cluster_; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        Prof prof(this, K_MESH, nb(2.0)); // HBM sees Q in and out once; everything else stays in shared memory
+        return ck(cudaLaunchKernelEx(&cfg, pma_relax_band_kernel, A), "cudaLaunchKernelEx(pma_relax_band)");
+      }
+    }
+    if (smem > (size_t)200 * 1024) return false;
     // one cluster: 16 CTAs (non-portable size, opt-in) when the device can schedule it, else 8
     if (relax_cluster_ == 0) {
       relax_cluster_ = -1;
@@ -1176,6 +1212,7 @@ class CudaOps : public DeviceOps {
   bool capturing_ = false;
   int64_t capture_launch0_ = 0, graph_replays_ = 0;
   cudaGraphExec_t graph_exec_ = nullptr;
+  int band_cluster_ = 0;  // pma_relax_band_kernel: 0 untried, -1 unavailable, else its cluster size
   int relax_cluster_ = 0; // 0 untried, -1 unavailable, else the cluster size of pma_relax_kernel
   int cycle_c_ = 0, cycle_pitch_ = 0, cycle_ext_ = 0; // sh_cycle_kernel: cluster size that fits (0 untried, -1 none), band sizes
   long long* cycle_prof_ = nullptr;
