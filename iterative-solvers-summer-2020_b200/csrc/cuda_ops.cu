@@ -80,6 +80,15 @@ class CudaOps : public DeviceOps {
   ~CudaOps() override {
     if (graph_exec_) { cudaStreamSynchronize(stream_); cudaGraphExecDestroy(graph_exec_); }
     if (cap_stream_) cudaStreamDestroy(cap_stream_);
+    if (relax_prof_) {
+      long long h[8] = {0};
+      cudaStreamSynchronize(stream_);
+      cudaMemcpy(h, relax_prof_, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[jfnk relax prof] clocks: sync1+pullQ=%lld metrics=%lld monitor=%lld sync2+pull+smooth=%lld "
+                      "wsum+sync3+rhs+rowDCT=%lld sync4+pull+colDCTs=%lld sync5+pull+rowDCT+update=%lld\n",
+              h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+      cudaFree(relax_prof_);
+    }
     if (cycle_prof_) { // JFNK_CYCLE_PROF=1: where the one-launch cycle kernel spends its clock cycles
       long long h[CP_COUNT] = {0};
       cudaStreamSynchronize(stream_);
@@ -997,6 +1006,10 @@ class CudaOps : public DeviceOps {
         at.id = cudaLaunchAttributeClusterDimension;
         at.val.clusterDim.x = band_cluster_; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
         cfg.attrs = &at; cfg.numAttrs = 1;
+        if (!relax_prof_ && getenv("JFNK_CYCLE_PROF") && atoi(getenv("JFNK_CYCLE_PROF")) != 0 &&
+            cudaMalloc(&relax_prof_, sizeof(long long) * 8) == cudaSuccess)
+          cudaMemsetAsync(relax_prof_, 0, sizeof(long long) * 8, stream_);
+        A.prof = relax_prof_;
         Prof prof(this, K_MESH, nb(2.0)); // HBM sees Q in and out once; everything else stays in shared memory
         return ck(cudaLaunchKernelEx(&cfg, pma_relax_band_kernel, A), "cudaLaunchKernelEx(pma_relax_band)");
       }
@@ -1216,6 +1229,7 @@ class CudaOps : public DeviceOps {
   int relax_cluster_ = 0; // 0 untried, -1 unavailable, else the cluster size of pma_relax_kernel
   int cycle_c_ = 0, cycle_pitch_ = 0, cycle_ext_ = 0; // sh_cycle_kernel: cluster size that fits (0 untried, -1 none), band sizes
   long long* cycle_prof_ = nullptr;
+  long long* relax_prof_ = nullptr;
   int cycle_cluster_[2] = {0, 0};                     // per operator: cluster size the device can schedule (-1: cannot)
   cudaStream_t cap_stream_ = nullptr, user_stream_ = nullptr;
   bool p2p_ = false;

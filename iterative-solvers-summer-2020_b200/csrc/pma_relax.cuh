@@ -33,6 +33,7 @@ struct RelaxArgs {
   double *a, *b, *t, *spec;
   const double *dctx, *dcty; // orthonormal DCT-II matrices (nx x nx, ny x ny)
   double* partials;       // one slot per CTA
+  long long* prof;        // optional (JFNK_CYCLE_PROF=1): clock cycles per phase of pma_relax_band_kernel, CTA 0
 };
 
 constexpr int kRelaxThreads = 512;

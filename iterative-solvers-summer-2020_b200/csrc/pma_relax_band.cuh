@@ -67,11 +67,39 @@ struct BandLayout {
     aown = take(rmax * nx); ae = take(a_rows * nx); be = take(a_rows * nx);
     t1own = take(rmax * nx); colbuf = take(ny * cmax); spec = take(ny * cmax); ucol = take(ny * cmax); urow = take(rmax * nx);
     mail = take(kBandMaxCluster);
-    // int tables (2 per double): Q pull, monitor pull, column pull, row pull
-    tabs = take((qe_rows * nx + a_rows * nx + ny * cmax + rmax * nx + 1) / 2 + 2);
+    // int tables (2 per double): Q pull, monitor pull, column pull, row pull, (row, column) of a band offset
+    tabs = take((2 * qe_rows * nx + a_rows * nx + ny * cmax + rmax * nx + 1) / 2 + 2);
     total = (size_t)o * sizeof(double);
   }
 };
+
+// One 8 x 8 tile of D = A . B on the fp64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA), operands read from shared memory
+// with arbitrary strides: A(m, k) = A[m sam + k sak], B(k, n) = B[k sbk + n sbn]; rows / columns / terms beyond M, N, K are
+// zero.  Fragment layout (PTX ISA, m8n8k4 .f64): lane = 4 g + t holds A(g, t), B(t, g) and the results D(g, 2t), D(g, 2t+1).
+// Two accumulator pairs on alternating k-steps halve the dependent chain.  The dense DCT products of the relaxation are
+// shared-memory-bandwidth bound on the CUDA cores (two loads per fma); a DMMA needs two loads per 8 fma.
+__device__ __forceinline__ void dmma_tile(const double* A, int sam, int sak, const double* B, int sbk, int sbn, int M, int N,
+                                          int K, int m0, int n0, double& d0, double& d1) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const bool mok = (m0 + g) < M, nok = (n0 + g) < N;
+  const double* ap = A + (size_t)(m0 + g) * sam + (size_t)t * sak;
+  const double* bp = B + (size_t)t * sbk + (size_t)(n0 + g) * sbn;
+  double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+  int k = 0;
+  for (; k + 8 <= K; k += 8) {
+    const double a0 = mok ? ap[(size_t)k * sak] : 0.0, b0 = nok ? bp[(size_t)k * sbk] : 0.0;
+    const double a1 = mok ? ap[(size_t)(k + 4) * sak] : 0.0, b1 = nok ? bp[(size_t)(k + 4) * sbk] : 0.0;
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(e0), "+d"(e1) : "d"(a1), "d"(b1));
+  }
+  for (; k < K; k += 4) {
+    const bool kok = (k + t) < K;
+    const double a0 = (mok && kok) ? ap[(size_t)k * sak] : 0.0, b0 = (nok && kok) ? bp[(size_t)k * sbk] : 0.0;
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
+  }
+  d0 = c0 + e0;
+  d1 = c1 + e1;
+}
 
 __global__ void __launch_bounds__(kBandThreads) pma_relax_band_kernel(const __grid_constant__ RelaxArgs A) {
   namespace cg = cooperative_groups;
@@ -83,8 +111,19 @@ __global__ void __launch_bounds__(kBandThreads) pma_relax_band_kernel(const __gr
   __shared__ int r0tab[kBandMaxCluster + 1], c0tab[kBandMaxCluster + 1];
   __shared__ double red[NW];
   __shared__ double total_s;
-  const MeshGeom& g = A.gm;
+  // the finite-difference weight tables next to the data: a cluster barrier invalidates L1, and a table entry fetched from
+  // L2 in front of every derivative would cost more than the derivative
+  __shared__ MeshTables tabs_s;
+  for (int i = tid; i < (int)(sizeof(MeshTables) / sizeof(double)); i += kBandThreads)
+    reinterpret_cast<double*>(&tabs_s)[i] = reinterpret_cast<const double*>(A.gm.tab)[i];
+  MeshGeom g = A.gm;
+  g.tab = &tabs_s;
   const int nx = g.nx, ny = g.ny;
+  const bool timing = (A.prof != nullptr) && blockIdx.x == 0 && tid == 0;
+  long long tlast = timing ? clock64() : 0;
+  auto tick = [&](int phase) {
+    if (timing) { const long long t = clock64(); A.prof[phase] += t - tlast; tlast = t; }
+  };
   const BandLayout L(nx, ny, C);
   double* Cys = band_smem + L.cy;
   double* Cxs = band_smem + L.cx;
@@ -116,6 +155,9 @@ __global__ void __launch_bounds__(kBandThreads) pma_relax_band_kernel(const __gr
   int* tabA = tabQ + L.qe_rows * nx;
   int* tabC = tabA + L.a_rows * nx;
   int* tabR = tabC + ny * cmax;
+  int* tabRC = tabR + L.rmax * nx;       // e -> (e / nx) << 16 | (e % nx): no integer division inside the passes
+  for (int e = tid; e < L.qe_rows * nx; e += kBandThreads) tabRC[e] = ((e / nx) << 16) | (e % nx);
+  const int mt_rows = (rows + 7) / 8, nt_x = (nx + 7) / 8, mt_y = (ny + 7) / 8, nt_c = (ncols + 7) / 8; // DMMA tiles
   const int nQ = (qr.hi - qr.lo) * nx, nA = (ar.hi - ar.lo) * nx, nC = ny * ncols, nR = rows * nx;
   for (int e = tid; e < nQ; e += kBandThreads) {
     const int r = qr.lo + e / nx, c = e % nx, o = owner_row(r);
@@ -165,15 +207,17 @@ __global__ void __launch_bounds__(kBandThreads) pma_relax_band_kernel(const __gr
     cl.sync(); // [1] every CTA's own rows of Q are current
     pull(QE, tabQ, nQ, Qown);
     __syncthreads();
+    tick(0);
     // metric fields of the current potential on the rows the Laplacian of the own rows reads
     for (int e = tid; e < (mr.hi - mr.lo) * nx; e += kBandThreads) {
-      const int r = mr.lo + e / nx, c = e % nx;
+      const int r = mr.lo + (tabRC[e] >> 16), c = tabRC[e] & 0xffff;
       mesh_metrics_point(g, Qv, r, c, Mv);
     }
     __syncthreads();
+    tick(1);
     // monitor function of the (old) solution on the own rows: |u_xx + u_yy|^2 or 1/(1+u)^6
     for (int e = tid; e < nR; e += kBandThreads) {
-      const int r = r0 + e / nx, c = e % nx;
+      const int r = r0 + (tabRC[e] >> 16), c = tabRC[e] & 0xffff;
       double lap = 0.0;
       if (A.pp.monitor_mode == 0) {
         double xx, yy;
@@ -182,6 +226,7 @@ __global__ void __launch_bounds__(kBandThreads) pma_relax_band_kernel(const __gr
       }
       Aown[e] = pma_monitor_point(A.pp.monitor_mode, Uv[(size_t)r * nx + c], lap);
     }
+    tick(2);
     cl.sync(); // [2]
     // smoothing sweeps on a band that shrinks by one row per sweep (ping-pong between AE and BE)
     pull(AE, tabA, nA, Aown);
@@ -193,13 +238,14 @@ __global__ void __launch_bounds__(kBandThreads) pma_relax_band_kernel(const __gr
       const double* av = a - (ptrdiff_t)ar.lo * nx;
       double* bv = b - (ptrdiff_t)ar.lo * nx;
       for (int e = tid; e < (sr.hi - sr.lo) * nx; e += kBandThreads) {
-        const int r = sr.lo + e / nx, c = e % nx;
+        const int r = sr.lo + (tabRC[e] >> 16), c = tabRC[e] & 0xffff;
         bv[(size_t)r * nx + c] = pma_smooth_point(g, av, r, c);
       }
       __syncthreads();
       double* tmp = a; a = b; b = tmp;
     }
     const double* mon = a - (ptrdiff_t)ar.lo * nx; // smoothed monitor, valid on the own rows
+    tick(3);
     // Mackenzie regularisation: sum mon |J| over the grid, then sqrt((mon + C sum |J| dksi deta) |J|) / alpha
     {
       double acc = 0.0;
@@ -233,45 +279,52 @@ __global__ void __launch_bounds__(kBandThreads) pma_relax_band_kernel(const __gr
       }
     }
     __syncthreads();
-    for (int e = tid; e < nR; e += kBandThreads) {
-      const int rr = e / nx, c = e % nx;
-      const double* xr = UROW + rr * nx;
-      const double* cr = Cxs + (size_t)c * nx;
-      double acc = 0.0;
-      for (int k = 0; k < nx; ++k) acc = fma(xr[k], cr[k], acc);
-      T1[e] = acc;
+    for (int tile = warp; tile < mt_rows * nt_x; tile += NW) { // T1 = rhs . Cx^T, one 8 x 8 tile per warp
+      const int m0 = (tile / nt_x) * 8, n0 = (tile % nt_x) * 8;
+      double d0, d1;
+      dmma_tile(UROW, nx, 1, Cxs, 1, nx, rows, nx, nx, m0, n0, d0, d1);
+      const int r = m0 + (lane >> 2), c = n0 + 2 * (lane & 3);
+      if (r < rows && c < nx) T1[r * nx + c] = d0;
+      if (r < rows && c + 1 < nx) T1[r * nx + c + 1] = d1;
     }
+    tick(4);
     cl.sync(); // [4] transpose: the column band of T1
     pull(COL, tabC, nC, T1);
     __syncthreads();
     // column transform, spectral divide: spec = (Cy . T1) / (1 - gamma Leig)
-    for (int e = tid; e < nC; e += kBandThreads) {
-      const int r = e / ncols, cc = e % ncols;
-      const double* cyr = Cys + (size_t)r * ny;
-      double acc = 0.0;
-      for (int k = 0; k < ny; ++k) acc = fma(cyr[k], COL[k * ncols + cc], acc);
-      SPEC[r * cmax + cc] = acc / inv[r * cmax + cc];
+    for (int tile = warp; tile < mt_y * nt_c; tile += NW) {
+      const int m0 = (tile / nt_c) * 8, n0 = (tile % nt_c) * 8;
+      double d0, d1;
+      dmma_tile(Cys, ny, 1, COL, ncols, 1, ny, ncols, ny, m0, n0, d0, d1);
+      const int r = m0 + (lane >> 2), c = n0 + 2 * (lane & 3);
+      if (r < ny && c < ncols) SPEC[r * cmax + c] = d0 / inv[r * cmax + c];
+      if (r < ny && c + 1 < ncols) SPEC[r * cmax + c + 1] = d1 / inv[r * cmax + c + 1];
     }
     __syncthreads();
     // inverse column transform: UCOL = Cy^T . spec
-    for (int e = tid; e < nC; e += kBandThreads) {
-      const int r = e / ncols, cc = e % ncols;
-      double acc = 0.0;
-      for (int k = 0; k < ny; ++k) acc = fma(Cys[(size_t)k * ny + r], SPEC[k * cmax + cc], acc);
-      UCOL[r * cmax + cc] = acc;
+    for (int tile = warp; tile < mt_y * nt_c; tile += NW) {
+      const int m0 = (tile / nt_c) * 8, n0 = (tile % nt_c) * 8;
+      double d0, d1;
+      dmma_tile(Cys, 1, ny, SPEC, cmax, 1, ny, ncols, ny, m0, n0, d0, d1);
+      const int r = m0 + (lane >> 2), c = n0 + 2 * (lane & 3);
+      if (r < ny && c < ncols) UCOL[r * cmax + c] = d0;
+      if (r < ny && c + 1 < ncols) UCOL[r * cmax + c + 1] = d1;
     }
+    tick(5);
     cl.sync(); // [5] transpose back: the own rows of UCOL
     pull(UROW, tabR, nR, UCOL);
     __syncthreads();
     // inverse row transform and the explicit Euler update: Q += dt (UROW . Cx)
-    for (int e = tid; e < nR; e += kBandThreads) {
-      const int rr = e / nx, c = e % nx;
-      const double* xr = UROW + rr * nx;
-      double acc = 0.0;
-      for (int k = 0; k < nx; ++k) acc = fma(xr[k], Cxs[(size_t)k * nx + c], acc);
+    for (int tile = warp; tile < mt_rows * nt_x; tile += NW) {
+      const int m0 = (tile / nt_x) * 8, n0 = (tile % nt_x) * 8;
+      double d0, d1;
+      dmma_tile(UROW, nx, 1, Cxs, nx, 1, rows, nx, nx, m0, n0, d0, d1);
+      const int r = m0 + (lane >> 2), c = n0 + 2 * (lane & 3);
       // Q.val += dt*Q.dt: product rounded, then sum (as the per-stage path and NumPy)
-      Qown[e] = combine(1.0 * Qown[e], A.dt, acc);
+      if (r < rows && c < nx) Qown[r * nx + c] = combine(1.0 * Qown[r * nx + c], A.dt, d0);
+      if (r < rows && c + 1 < nx) Qown[r * nx + c + 1] = combine(1.0 * Qown[r * nx + c + 1], A.dt, d1);
     }
+    tick(6);
   }
   __syncthreads();
   for (int e = tid; e < nR; e += kBandThreads) A.Q[(size_t)r0 * nx + e] = Qown[e];
