@@ -13,6 +13,7 @@
 
 #include "backend.h"
 #include "blas_kernels.cuh"
+#include "dct_fft.cuh"
 #include "mesh_kernels.cuh"
 #include "mesh_march.cuh"
 #include "pma_kernels.cuh"
@@ -32,11 +33,11 @@ inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 // kernel classes of the per-kernel timing (bench.py roofline); bytes are the ALGORITHMIC bytes of DESIGN.md
 enum KClass { K_MDOT = 0, K_GS_UPDATE, K_MAXPY, K_LINCOMB, K_SPMV_LAP, K_SPMV_L, K_SET_PREV, K_RESIDUAL, K_JVP,
-              K_SHLIN, K_MESH, K_SCALAR, K_MDOT2, K_GS_UPDATE2, K_HALO, K_ALLREDUCE, K_CYCLE, K_MESH_LAP, K_MESH_FLUX, K_MESH_DIV, K_COUNT };
+              K_SHLIN, K_MESH, K_SCALAR, K_MDOT2, K_GS_UPDATE2, K_HALO, K_ALLREDUCE, K_CYCLE, K_MESH_LAP, K_MESH_FLUX, K_MESH_DIV, K_MARCH, K_DCT, K_COUNT };
 const char* const kClassName[K_COUNT] = {"mdot", "gs_update", "maxpy", "lincomb", "spmv_lap", "spmv_L", "set_prev",
                                          "sh_residual", "sh_jvp", "shlin", "mesh", "scalar", "mdot_pass2",
                                          "gs_update_pass2", "halo_exchange", "allreduce", "lgmres_cycle", "mesh_lap", "mesh_flux",
-                                         "mesh_div"};
+                                         "mesh_div", "mesh_march", "dct"};
 
 class CudaOps : public DeviceOps {
  public:
@@ -103,6 +104,8 @@ class CudaOps : public DeviceOps {
     for (auto& r : recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : free_events_) cudaEventDestroy(e);
     for (int i = 0; i < 6; i += 2) if (halo_[i]) cudaFree(halo_[i]);
+    if (fftW_[1] && fftW_[1] != fftW_[0]) { cudaFree(fftW_[1]); cudaFree(fftWq_[1]); }
+    if (fftW_[0]) { cudaFree(fftW_[0]); cudaFree(fftWq_[0]); }
     if (dtab_) cudaFree(dtab_);
     if (dctx_) cudaFree(dctx_);
     if (dcty_) cudaFree(dcty_);
@@ -810,7 +813,7 @@ class CudaOps : public DeviceOps {
     const int nchunks = (rows + A.rows_per_chunk - 1) / A.rows_per_chunk;
     static const int dbg = getenv("JFNK_MARCH_DEBUG") ? atoi(getenv("JFNK_MARCH_DEBUG")) : 0;
     A.debug_skip = (MODE == MARCH_PMA2_RESID) ? 0 : dbg; // (the reduction of RESID needs every CTA)
-    Prof prof(this, K_MESH, nb(vecs));
+    Prof prof(this, K_MARCH, nb(vecs));
     mesh_march_kernel<MODE, HAS_V><<<A.nframe_ctas + A.nstrips * nchunks, kMarchThreads, smem, stream_>>>(A, S_, ws_);
   }
   MarchArgs march_args(const double* const* M, const double* x, const double* v, ScalarRef a, double* out) {
@@ -963,9 +966,11 @@ class CudaOps : public DeviceOps {
   // persistent single-cluster kernel for the reference-sized grids (pma_relax.cuh); JFNK_RELAX_FUSED=0 disables
   bool mesh_relax_fused(const MeshParams& mp, const PmaParams& pp, double* Q, const double* Uval, double dt, int loops,
                         int deriv_bc, double* const* M, double* a, double* b, double* t, double* spec) override {
-    static const bool off = getenv("JFNK_RELAX_FUSED") && atoi(getenv("JFNK_RELAX_FUSED")) == 0;
+    const char* env_fused = getenv("JFNK_RELAX_FUSED"); // (read per call: the parity tests flip it)
+    const bool off = env_fused && atoi(env_fused) == 0;
     const size_t smem = sizeof(double) * ((size_t)g_.nx * g_.nx + (size_t)g_.ny * g_.ny + g_.n());
     if (off || capturing_ || loops < 1) return false;
+    if ((size_t)g_.nx * g_.nx + (size_t)g_.ny * g_.ny > (size_t)28 * 1024) return false; // both DCT matrices must fit in shared memory
     if (!ensure_dct()) return false;
     RelaxArgs A;
     memset(&A, 0, sizeof(A));
@@ -1044,8 +1049,57 @@ class CudaOps : public DeviceOps {
     Prof prof(this, K_MESH, nb(30.0) * loops);
     return ck(cudaLaunchKernelEx(&cfg, pma_relax_kernel, A), "cudaLaunchKernelEx(pma_relax)");
   }
+  // ---- FFT-based DCT (dct_fft.cuh): power-of-two grids from 64 to 8192 points per side ----
+  static int log2_exact(int n) { int l = 0; while ((1 << l) < n) ++l; return (1 << l) == n ? l : -1; }
+  bool fft_dct_ok() const {
+    const char* env = getenv("JFNK_DCT_FFT"); // (read per call: the parity tests flip it)
+    const bool off = env && atoi(env) == 0;
+    return !off && log2_exact(g_.nx) >= 6 && log2_exact(g_.ny) >= 6 && g_.nx <= 8192 && g_.ny <= 8192;
+  }
+  bool ensure_fft_tables() {
+    for (int d = 0; d < 2; ++d) {
+      const int N = d == 0 ? g_.nx : g_.ny;
+      if (fftW_[d]) continue;
+      if (d == 1 && g_.ny == g_.nx) { fftW_[1] = fftW_[0]; fftWq_[1] = fftWq_[0]; continue; }
+      if (!ck(cudaMalloc(&fftW_[d], sizeof(double2) * (N / 2)), "cudaMalloc(fft twiddles)")) return false;
+      if (!ck(cudaMalloc(&fftWq_[d], sizeof(double2) * N), "cudaMalloc(fft twiddles)")) return false;
+      dct_twiddle_kernel<<<(N + 255) / 256, 256, 0, stream_>>>(N, fftW_[d], fftWq_[d]);
+      launches_++;
+    }
+    return true;
+  }
+  // out = DCT (inverse: inverse DCT) of every row of the rows x N field `in`
+  void fft_rows(int rows, int N, int dim, const double* in, double* out, int inverse) {
+    const size_t smem = sizeof(double2) * (size_t)(N + N / 2);
+    int& per_sm = occupancy_[inverse ? reinterpret_cast<const void*>(dct_fft_rows_kernel<true>)
+                                     : reinterpret_cast<const void*>(dct_fft_rows_kernel<false>)];
+    if (per_sm == 0 || smem > fft_smem_set_) {
+      ck(cudaFuncSetAttribute(dct_fft_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, fft_smem_set_)), "cudaFuncSetAttribute(fft smem)");
+      ck(cudaFuncSetAttribute(dct_fft_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, fft_smem_set_)), "cudaFuncSetAttribute(fft smem)");
+      fft_smem_set_ = std::max(smem, fft_smem_set_);
+      per_sm = 4;
+    }
+    const int blocks = (int)std::min<long long>(rows, (long long)sms_ * 4);
+    const int logN = log2_exact(N);
+    Prof prof(this, K_DCT, 16.0 * (double)rows * N);
+    if (inverse) dct_fft_rows_kernel<true><<<blocks, kFftThreads, smem, stream_>>>(N, logN, rows, in, out, fftW_[dim], fftWq_[dim]);
+    else dct_fft_rows_kernel<false><<<blocks, kFftThreads, smem, stream_>>>(N, logN, rows, in, out, fftW_[dim], fftWq_[dim]);
+  }
+  void transpose(int rows, int cols, const double* in, double* out) {
+    const long long tiles = (long long)((cols + 31) / 32) * ((rows + 31) / 32);
+    Prof prof(this, K_DCT, 16.0 * (double)rows * cols);
+    transpose_kernel<<<(int)std::min<long long>(tiles, (long long)sms_ * 8), 256, 0, stream_>>>(rows, cols, in, out);
+  }
   void pma_dct2(const double* in, double* tmp, double* out, int inverse) override {
     const int nx = g_.nx, ny = g_.ny;
+    if (fft_dct_ok() && ensure_fft_tables()) {
+      // rows (ksi direction), transpose, rows again (eta direction), transpose back: 4 reads + 4 writes of the field
+      fft_rows(ny, nx, 0, in, tmp, inverse);
+      transpose(ny, nx, tmp, out);
+      fft_rows(nx, ny, 1, out, tmp, inverse);
+      transpose(nx, ny, tmp, out);
+      return;
+    }
     if (!ensure_dct()) return;
     if (!inverse) {
       gemm(ny, nx, ny, dcty_, 0, in, 0, tmp);  // Cy . X
@@ -1212,6 +1266,8 @@ class CudaOps : public DeviceOps {
   MeshTables* dtab_ = nullptr;
   bool tab_valid_ = false;
   MeshParams last_mp_ = {1.0, 1.0, 0, 0, 0, 0};
+  double2 *fftW_[2] = {nullptr, nullptr}, *fftWq_[2] = {nullptr, nullptr}; // twiddle tables of the FFT-based DCT (nx, ny)
+  size_t fft_smem_set_ = 0;
   double *dctx_ = nullptr, *dcty_ = nullptr; // orthonormal DCT-II matrices (nx x nx, ny x ny), built on first use
   SHParams shp_;
   int64_t launches_ = 0;

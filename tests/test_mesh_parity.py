@@ -366,3 +366,35 @@ def test_lgmres_restarts_on_mesh_problems(buffers, model):
     r = b - jac.matvec(xg)
     assert np.linalg.norm(r) <= 2e-4 * np.linalg.norm(b)
     assert rel(xg, xs) < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [128, 256])
+def test_fft_dct_mesh_update_matches_scipy_fft(monkeypatch, N):
+    """solve_PMA (PMA2_nk.py:393-403) transforms with scipy.fft.dct / idct(norm="ortho").  On power-of-two grids the
+    engine uses its own FFT-based DCT (csrc/dct_fft.cuh: Makhoul permutation + shared-memory radix-2 FFT per row,
+    transposes for the column direction) instead of the dense DCT-matrix products; both against the oracle's scipy.fft
+    path, on the increment of one mesh update."""
+    xi = np.linspace(-1, 1, N)
+    X, Y = np.meshgrid(xi, xi)
+    Q = np.reshape(0.5 * X ** 2 + 0.5 * Y ** 2 + 0.01 * np.cos(np.pi * X) * np.cos(np.pi * Y), N * N)
+    U = np.reshape(-0.3 * np.exp(-4 * (X ** 2 + Y ** 2)), N * N)
+    po = PMA2Oracle(N=N)
+    po.set_mesh(Q)
+    po.Uval = U.copy()
+    Qdt = po.ops.solve_pma(po.monitor(), po.met["J"], po.alpha, po.gamma)
+    monkeypatch.setenv("JFNK_RELAX_FUSED", "0")  # the per-stage path (what a 2048^2 grid runs)
+    got = {}
+    for fft in ("1", "0"):
+        monkeypatch.setenv("JFNK_DCT_FFT", fft)
+        P = jf.PMA2Residual(N=N)
+        got[fft] = P.relax_mesh(Q, U, 1e-4, loops=1) - Q
+        assert rel(got[fft], 1e-4 * Qdt) < 1e-11, fft
+    assert rel(got["1"], got["0"]) < 1e-12
+    # several passes (ping-pong buffers, CUDA-graph replay of the recorded pass)
+    monkeypatch.setenv("JFNK_DCT_FFT", "1")
+    P = jf.PMA2Residual(N=N)
+    Q5 = P.relax_mesh(Q, U, 1e-5, loops=6)
+    monkeypatch.setenv("JFNK_DCT_FFT", "0")
+    P0 = jf.PMA2Residual(N=N)
+    assert rel(Q5 - Q, P0.relax_mesh(Q, U, 1e-5, loops=6) - Q) < 1e-11
