@@ -24,6 +24,7 @@
 #include "sh_kernels.cuh"
 #include "sh_box_kernel.cuh"
 #include "sh_cycle.cuh"
+#include "mesh_cycle.cuh"
 
 namespace jfnk {
 
@@ -414,9 +415,62 @@ class CudaOps : public DeviceOps {
     cudaGetLastError();
     return cs;
   }
+  // droplet problem: mesh_cycle.cuh
+  bool mesh_cycle_fused(const FusedCycleIn& in, FusedCycleOut& out) {
+    if (variant_ != 0 || g_.nranks != 1 || capturing_ || in.m_max + 1 > JF_MAXV || g_.ny < 2 * kMcCluster || g_.nx < 8) return false;
+    const size_t need_max = MeshCycleLayout(g_.nx, g_.ny, in.m_max).total;
+    if (need_max > (size_t)226 * 1024) return false;
+    if (mesh_cycle_ok_ == 0) {
+      mesh_cycle_ok_ = -1;
+      if (cudaFuncSetAttribute(mesh_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_max) == cudaSuccess) {
+        cudaFuncSetAttribute(mesh_cycle_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kMcCluster); cfg.blockDim = dim3(kMcThreads); cfg.dynamicSmemBytes = need_max;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = kMcCluster; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, mesh_cycle_kernel, &cfg) == cudaSuccess && nclusters >= 1) mesh_cycle_ok_ = 1;
+      }
+      cudaGetLastError();
+    }
+    if (mesh_cycle_ok_ < 0) return false;
+    MeshCycleArgs A;
+    memset(&A, 0, sizeof(A));
+    A.gm = geom(*in.mp);
+    A.dp = *in.dp;
+    A.m = in.m; A.k = in.k; A.gs_mode = in.gs_mode;
+    A.omega = in.omega; A.ptol = in.ptol; A.tau2 = in.tau2; A.v0n2 = in.v0n2;
+    A.x0 = in.x0; A.f0 = in.f0; A.v0 = in.v0; A.uval = in.uval; A.fprev = in.fprev;
+    A.M = cptrs(in.M);
+    for (int j = 0; j < in.k; ++j) { A.ov[j] = in.ov[j]; A.ov_zn2[j] = in.ov_zn2[j]; }
+    A.out = in.out; A.out_zn2 = in.out_zn2; A.S = S_;
+    const bool trial = in.trial_x && in.trial_F;
+    if (trial) { A.trial_x = in.trial_x; A.trial_F = in.trial_F; A.trial_norm_off = in.trial_norm_off; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kMcCluster); cfg.blockDim = dim3(kMcThreads);
+    cfg.dynamicSmemBytes = MeshCycleLayout(g_.nx, g_.ny, in.m).total; cfg.stream = stream_;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = kMcCluster; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    {
+      Prof prof(this, K_CYCLE, nb(12.0 + in.k + (trial ? 6.0 : 0.0)));
+      if (!ck(cudaLaunchKernelEx(&cfg, mesh_cycle_kernel, A), "cudaLaunchKernelEx(mesh_cycle)")) return true;
+    }
+    double rec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    read_scalars(JS_CYC, 8, rec);
+    out.nit = (int)rec[0]; out.reorth = (int)rec[1]; out.res = rec[2]; out.flags = (int)rec[3]; out.dxn2 = rec[4];
+    out.has_trial = trial ? 1 : 0;
+    out.trial_nrm[0] = rec[5]; out.trial_nrm[1] = rec[6]; out.trial_nrm[2] = rec[7];
+    return true;
+  }
   bool cycle_fused(const FusedCycleIn& in, FusedCycleOut& out) override {
     const char* env = getenv("JFNK_CYCLE_FUSED"); // (read per cycle: the parity tests flip it)
     const bool off = env && atoi(env) == 0;
+    if (!off && in.kind == 2) return mesh_cycle_fused(in, out);
+    if (in.kind != 0) return false;
     if (off || variant_ != 0 || g_.nranks != 1 || capturing_ || in.m_max + 1 > JF_MAXV) return false;
     // cluster size: 16 CTAs when every CTA gets at least one row and the bands fit, else 8
     if (cycle_c_ == 0) {
@@ -1283,6 +1337,7 @@ class CudaOps : public DeviceOps {
   cudaGraphExec_t graph_exec_ = nullptr;
   int band_cluster_ = 0;  // pma_relax_band_kernel: 0 untried, -1 unavailable, else its cluster size
   int relax_cluster_ = 0; // 0 untried, -1 unavailable, else the cluster size of pma_relax_kernel
+  int mesh_cycle_ok_ = 0;                             // mesh_cycle_kernel: 0 untried, -1 cannot be scheduled, 1 ok
   int cycle_c_ = 0, cycle_pitch_ = 0, cycle_ext_ = 0; // sh_cycle_kernel: cluster size that fits (0 untried, -1 none), band sizes
   long long* cycle_prof_ = nullptr;
   long long* relax_prof_ = nullptr;
