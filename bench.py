@@ -347,7 +347,8 @@ def main():
                "h2d_bytes_per_step": int(8 * N * N), "d2h_bytes_per_step": int(8 * N * N),
                "call": "U = SHResidual.steps(U_ndarray, 1)  (page-locked NumPy arrays in and out)",
                "h2d_ms": round(h2d_ms, 2), "d2h_ms": round(d2h_ms, 2),
-               "h2d_GBps": round(nb_ / (h2d_ms * 1e-3) / 1e9, 1), "d2h_GBps": round(nb_ / (d2h_ms * 1e-3) / 1e9, 1)}
+               "h2d_GBps": round(nb_ / (h2d_ms * 1e-3) / 1e9, 1), "d2h_GBps": round(nb_ / (d2h_ms * 1e-3) / 1e9, 1),
+               "host_numa_bound_cpus": (len(comm.cpus) if (comm is not None and comm.cpus) else None)}
         U = torch.from_numpy(Uh).to("cuda")
 
     # ---- standalone stencil SpMV bandwidth on the same grid (BASELINE metric, config 5 at this size) ---------

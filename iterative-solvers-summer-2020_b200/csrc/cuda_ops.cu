@@ -415,15 +415,17 @@ class CudaOps : public DeviceOps {
     cudaGetLastError();
     return cs;
   }
-  // droplet problem: mesh_cycle.cuh
+  // droplet / PMA2 on the reference's grids: mesh_cycle.cuh
+  template <int KIND>
   bool mesh_cycle_fused(const FusedCycleIn& in, FusedCycleOut& out) {
     if (variant_ != 0 || g_.nranks != 1 || capturing_ || in.m_max + 1 > JF_MAXV || g_.ny < 2 * kMcCluster || g_.nx < 8) return false;
-    const size_t need_max = MeshCycleLayout(g_.nx, g_.ny, in.m_max).total;
+    const size_t need_max = MeshCycleLayout(g_.nx, g_.ny, in.m_max, KIND).total;
     if (need_max > (size_t)226 * 1024) return false;
-    if (mesh_cycle_ok_ == 0) {
-      mesh_cycle_ok_ = -1;
-      if (cudaFuncSetAttribute(mesh_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_max) == cudaSuccess) {
-        cudaFuncSetAttribute(mesh_cycle_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    int& ok = mesh_cycle_ok_[KIND];
+    if (ok == 0) {
+      ok = -1;
+      if (cudaFuncSetAttribute(mesh_cycle_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_max) == cudaSuccess) {
+        cudaFuncSetAttribute(mesh_cycle_kernel<KIND>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(kMcCluster); cfg.blockDim = dim3(kMcThreads); cfg.dynamicSmemBytes = need_max;
         cudaLaunchAttribute at;
@@ -431,15 +433,15 @@ class CudaOps : public DeviceOps {
         at.val.clusterDim.x = kMcCluster; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
         cfg.attrs = &at; cfg.numAttrs = 1;
         int nclusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&nclusters, mesh_cycle_kernel, &cfg) == cudaSuccess && nclusters >= 1) mesh_cycle_ok_ = 1;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, mesh_cycle_kernel<KIND>, &cfg) == cudaSuccess && nclusters >= 1) ok = 1;
       }
       cudaGetLastError();
     }
-    if (mesh_cycle_ok_ < 0) return false;
+    if (ok < 0) return false;
     MeshCycleArgs A;
     memset(&A, 0, sizeof(A));
     A.gm = geom(*in.mp);
-    A.dp = *in.dp;
+    if (KIND == MC_DROPLET) A.dp = *in.dp; else A.pp = *in.pp;
     A.m = in.m; A.k = in.k; A.gs_mode = in.gs_mode;
     A.omega = in.omega; A.ptol = in.ptol; A.tau2 = in.tau2; A.v0n2 = in.v0n2;
     A.x0 = in.x0; A.f0 = in.f0; A.v0 = in.v0; A.uval = in.uval; A.fprev = in.fprev;
@@ -450,14 +452,14 @@ class CudaOps : public DeviceOps {
     if (trial) { A.trial_x = in.trial_x; A.trial_F = in.trial_F; A.trial_norm_off = in.trial_norm_off; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kMcCluster); cfg.blockDim = dim3(kMcThreads);
-    cfg.dynamicSmemBytes = MeshCycleLayout(g_.nx, g_.ny, in.m).total; cfg.stream = stream_;
+    cfg.dynamicSmemBytes = MeshCycleLayout(g_.nx, g_.ny, in.m, KIND).total; cfg.stream = stream_;
     cudaLaunchAttribute at;
     at.id = cudaLaunchAttributeClusterDimension;
     at.val.clusterDim.x = kMcCluster; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
     {
       Prof prof(this, K_CYCLE, nb(12.0 + in.k + (trial ? 6.0 : 0.0)));
-      if (!ck(cudaLaunchKernelEx(&cfg, mesh_cycle_kernel, A), "cudaLaunchKernelEx(mesh_cycle)")) return true;
+      if (!ck(cudaLaunchKernelEx(&cfg, mesh_cycle_kernel<KIND>, A), "cudaLaunchKernelEx(mesh_cycle)")) return true;
     }
     double rec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     read_scalars(JS_CYC, 8, rec);
@@ -469,7 +471,8 @@ class CudaOps : public DeviceOps {
   bool cycle_fused(const FusedCycleIn& in, FusedCycleOut& out) override {
     const char* env = getenv("JFNK_CYCLE_FUSED"); // (read per cycle: the parity tests flip it)
     const bool off = env && atoi(env) == 0;
-    if (!off && in.kind == 2) return mesh_cycle_fused(in, out);
+    if (!off && in.kind == 2) return mesh_cycle_fused<MC_DROPLET>(in, out);
+    if (!off && in.kind == 3) return mesh_cycle_fused<MC_PMA2>(in, out);
     if (in.kind != 0) return false;
     if (off || variant_ != 0 || g_.nranks != 1 || capturing_ || in.m_max + 1 > JF_MAXV) return false;
     // cluster size: 16 CTAs when every CTA gets at least one row and the bands fit, else 8
@@ -1337,7 +1340,7 @@ class CudaOps : public DeviceOps {
   cudaGraphExec_t graph_exec_ = nullptr;
   int band_cluster_ = 0;  // pma_relax_band_kernel: 0 untried, -1 unavailable, else its cluster size
   int relax_cluster_ = 0; // 0 untried, -1 unavailable, else the cluster size of pma_relax_kernel
-  int mesh_cycle_ok_ = 0;                             // mesh_cycle_kernel: 0 untried, -1 cannot be scheduled, 1 ok
+  int mesh_cycle_ok_[2] = {0, 0};                             // mesh_cycle_kernel: 0 untried, -1 cannot be scheduled, 1 ok
   int cycle_c_ = 0, cycle_pitch_ = 0, cycle_ext_ = 0; // sh_cycle_kernel: cluster size that fits (0 untried, -1 none), band sizes
   long long* cycle_prof_ = nullptr;
   long long* relax_prof_ = nullptr;

@@ -64,7 +64,7 @@ struct PmaParams; // mesh_math.h
 
 // One whole LGMRES inner cycle in one launch (Engine::cycle -> DeviceOps::cycle_fused; CUDA: sh_cycle.cuh)
 struct FusedCycleIn {
-  int kind;              // 0: Swift-Hohenberg (fields below) ; 2: droplet (mesh fields at the end)
+  int kind;              // 0: Swift-Hohenberg (fields below) ; 2: droplet, 3: PMA2 (mesh fields at the end)
   int linear;            // 0: FD Jacobian of the Swift-Hohenberg residual about x0 ; 1: the linearly-implicit operator
   const double* x0;      // linearisation point (null when linear)
   const double* g0;      // G(x0) ; linear: the diagonal D
@@ -84,6 +84,7 @@ struct FusedCycleIn {
   // droplet (kind 2): geometry, parameters, the 7 metric fields, previous time level, its Crank-Nicolson term, F(x0)
   const MeshParams* mp;
   const DropletParams* dp;
+  const Pma2Params* pp;
   const double* const* M;
   const double *uval, *fprev, *f0;
 };

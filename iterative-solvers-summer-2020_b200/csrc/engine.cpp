@@ -437,15 +437,15 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
   // Reference-sized Swift-Hohenberg grids: the whole cycle (Arnoldi process, least squares, dx assembly) is ONE launch of a
   // single thread-block cluster that keeps the basis in shared memory (sh_cycle.cuh); the host reads one record.
   bool fused = false;
-  const bool droplet = (cfg_.problem == JFNK_PROBLEM_DROPLET);
-  if (!psolve_ && (((cfg_.problem == JFNK_PROBLEM_SH || linear_op_) && (linear_op_ || g0_)) || (droplet && f0_))) {
+  const bool droplet = (cfg_.problem == JFNK_PROBLEM_DROPLET), pma2 = (cfg_.problem == JFNK_PROBLEM_PMA2);
+  if (!psolve_ && (((cfg_.problem == JFNK_PROBLEM_SH || linear_op_) && (linear_op_ || g0_)) || ((droplet || pma2) && f0_))) {
     FusedCycleIn in;
     memset(&in, 0, sizeof(in));
-    in.kind = droplet ? 2 : 0;
+    in.kind = droplet ? 2 : (pma2 ? 3 : 0);
     in.linear = linear_op_ ? 1 : 0;
     in.x0 = linear_op_ ? nullptr : x0_;
     in.g0 = linear_op_ ? D_ : g0_;
-    if (droplet) { in.mp = &mp_; in.dp = &dp_; in.M = MF_; in.uval = UVAL_; in.fprev = CN_; in.f0 = f0_; }
+    if (droplet || pma2) { in.mp = &mp_; in.dp = &dp_; in.pp = &pp_; in.M = MF_; in.uval = UVAL_; in.fprev = CN_; in.f0 = f0_; }
     in.v0 = v0vec; in.v0n2 = v0n2; in.omega = omega_; in.ptol = ptol; in.tau2 = tau2;
     in.gs_mode = cfg_.gs_mode; in.m = m; in.k = k; in.m_max = cfg_.inner_m + cfg_.outer_k;
     for (int j = 0; j < k; ++j) { in.ov[j] = OV_[ov_slots_[j]]; in.ov_zn2[j] = JS_ZN2 + ov_slots_[j]; }

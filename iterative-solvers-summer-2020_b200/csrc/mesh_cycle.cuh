@@ -1,7 +1,7 @@
 // One whole LGMRES inner cycle of the droplet problem (droplet.py:383 -> _fgmres, _gcrotmk.py:16-183, plus the solution
 // assembly of lgmres.py:188-208 and the first line-search trial of the Newton step that follows) as ONE launch of one
 // 16-CTA thread-block cluster -- the moving-mesh counterpart of sh_cycle.cuh, for the reference's droplet grids
-// (61 x 61 ... 91 x 61).
+// (61 x 61 ... 91 x 61) and, with a two-stage operator, for PMA2_nk.py's own 51 x 51 grid (KIND 1, below).
 //
 // The streaming path needs five dependent launches per Arnoldi step (Laplacian + pressure, flux, divergence + quotient,
 // multi-dot, update) of ~10 us each on 5551 points: 57 us per residual evaluation, all latency.  Here every CTA owns a band of
@@ -18,6 +18,9 @@
 // followed by the classical Gram-Schmidt step of sh_cycle.cuh (all dots in one DSMEM exchange, update + norm in another,
 // replicated Givens / stopping decisions from hd_math.h): four cluster barriers per Arnoldi step, no global-memory
 // round trip between the stages, one launch and one read-back per Newton iteration.
+//
+// KIND 1 -- PMA2 (PMA2_nk.py:121-159): F(t) = (t - uval)/dt - (rhs(t, Lap Lap t) + cn)/2 is two stencil stages,
+//   lap1 = Lap T own rows -> cluster barrier, pull +-3 rows ; w = (F(T, Lap lap1) - f0)/omega  (boundary rhs zeroed).
 #pragma once
 #include <cooperative_groups.h>
 #include "cuda_common.cuh"
@@ -31,9 +34,12 @@ constexpr int kMcThreads = 512;
 constexpr int kMcCluster = 16;
 constexpr int kMcWarps = kMcThreads / 32;
 
+enum MeshCycleKind { MC_DROPLET = 0, MC_PMA2 = 1 };
+
 struct MeshCycleArgs {
   MeshGeom gm;
   DropletParams dp;
+  Pma2Params pp;
   int m, k, gs_mode;
   double omega, ptol, tau2, v0n2;
   const double* x0;   // linearisation point
@@ -57,7 +63,8 @@ struct MeshCycleLayout {
   int arena, mailD, mailN, mailX, cf, te, a22e, a12e, own5, pown, pe, aown, bown, be, f0, tab, v;
   int rmax, t_rows, e_rows, pitch;
   size_t total;
-  __host__ __device__ MeshCycleLayout(int nx, int ny, int m) {
+  // kind 0 (droplet): p / A / B bands with +-2 rows ; kind 1 (PMA2): `pe` holds lap1 with the +-3 rows of the t band
+  __host__ __device__ MeshCycleLayout(int nx, int ny, int m, int kind) {
     rmax = (ny + kMcCluster - 1) / kMcCluster;
     // ext(own, H) spans at most rows + 2H rows; the widening to the closure stencils only applies to ranges that end
     // below row 6 / start above row ny - 6, i.e. to at most 6 rows
@@ -72,8 +79,8 @@ struct MeshCycleLayout {
     te = take(t_rows * nx);
     a22e = take(e_rows * nx); a12e = take(e_rows * nx);
     own5 = take(5 * pitch);   // A11, J, Q_xx, Q_yy, Q_xy on the own rows
-    pown = take(pitch); pe = take(e_rows * nx);   // (pe doubles as the extended band of A)
-    aown = take(pitch); bown = take(pitch); be = take(e_rows * nx);
+    pown = take(pitch); pe = take((kind == 1 ? t_rows : e_rows) * nx);   // (pe doubles as the extended band of A)
+    aown = take(kind == 1 ? 0 : pitch); bown = take(kind == 1 ? 0 : pitch); be = take(kind == 1 ? 0 : e_rows * nx);
     f0 = take(pitch);
     tab = take((t_rows * nx + 1) / 2 + 1);        // int table of the largest extended band: owner << 20 | offset
     v = take((m + 1) * pitch);
@@ -81,6 +88,7 @@ struct MeshCycleLayout {
   }
 };
 
+template <int KIND>
 __global__ void __launch_bounds__(kMcThreads) mesh_cycle_kernel(const __grid_constant__ MeshCycleArgs A) {
   namespace cg = cooperative_groups;
   cg::cluster_group cl = cg::this_cluster(); // the whole grid is one cluster
@@ -97,7 +105,7 @@ __global__ void __launch_bounds__(kMcThreads) mesh_cycle_kernel(const __grid_con
   MeshGeom g = A.gm;
   g.tab = &tabs_s;
   const int nx = g.nx, ny = g.ny, k = A.k, m = A.m;
-  const MeshCycleLayout L(nx, ny, m);
+  const MeshCycleLayout L(nx, ny, m, KIND);
   double* Ssm = mc_smem + L.arena;
   double* mailD = mc_smem + L.mailD;
   double* mailN = mc_smem + L.mailN;
@@ -197,9 +205,32 @@ __global__ void __launch_bounds__(kMcThreads) mesh_cycle_kernel(const __grid_con
       const int rr = p / nx, c = p - rr * nx, r = r0 + rr;
       double xx, yy;
       mesh_laplace_point(g, Mv, Tv, r, c, 0, xx, yy);
-      Pown[p] = droplet_pressure_point(A.dp, Tv[(size_t)r * nx + c], xx + yy);
+      Pown[p] = (KIND == MC_PMA2) ? xx + yy : droplet_pressure_point(A.dp, Tv[(size_t)r * nx + c], xx + yy);
     }
     cl.sync();
+    if (KIND == MC_PMA2) {
+      // second stage: Laplacian of lap1 (pulled with the +-3 rows of the t band), pointwise rhs, Crank-Nicolson combination
+      pull(PE, tabT, nT, Pown);
+      __syncthreads();
+      const double* L1v = PE - (ptrdiff_t)tr.lo * nx;
+      for (int p = tid; p < Pn; p += kMcThreads) {
+        const int rr = p / nx, c = p - rr * nx, r = r0 + rr;
+        double xx, yy;
+        mesh_laplace_point(g, Mv, L1v, r, c, 0, xx, yy);
+        const bool bdy = (r == 0 || c == 0 || r == ny - 1 || c == nx - 1);
+        const double u = Tv[(size_t)r * nx + c];
+        const double rhs = bdy ? 0.0 : pma2_rhs_point(A.pp, u, xx + yy);
+        const double f = pma2_combine_point(A.pp, u, A.uval[goff + p], rhs, A.fprev[goff + p]);
+        if (quot) W[p] = (f - F0[p]) / scale;
+        else {
+          A.trial_F[goff + p] = f;
+          A.trial_x[goff + p] = u;
+          nrm[0] = fma(f, f, nrm[0]); nrm[1] = fmax(nrm[1], fabs(f)); nrm[2] = fmax(nrm[2], fabs(u));
+        }
+      }
+      __syncthreads();
+      return;
+    }
     pull(PE, tabE, nE, Pown);
     __syncthreads();
     for (int p = tid; p < Pn; p += kMcThreads) {

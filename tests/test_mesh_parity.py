@@ -441,3 +441,36 @@ def test_one_launch_droplet_cycle_matches_streaming_path(monkeypatch, grid, gs, 
     #  stiffest shipped state -- measured 1.3e-9 on the 81 x 61 one, 1e-10 on the others)
     assert rel(out["1"][0], out["0"][0]) < 3e-9
     assert out["1"][2] < out["0"][2] / 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gs,tau", [("cgs-ifneeded", 0.25), ("cgs-ifneeded", 0.97)])
+def test_one_launch_pma2_cycle_matches_streaming_path(monkeypatch, gs, tau):
+    """PMA2_nk.py's own 51 x 51 grid through the two-stage operator of csrc/mesh_cycle.cuh (Lap, pull, Lap + pointwise terms)
+    against the streaming kernels, three steps of the script's loop (mesh update included)."""
+    N, k = 51, 1e-4
+    xi = np.linspace(-1, 1, N)
+    X, Y = np.meshgrid(xi, xi)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("JFNK_CYCLE_FUSED", fused)
+        F = jf.PMA2Residual(N=N, gs=gs, gs_tau=tau)
+        Q = np.reshape(0.5 * X ** 2 + 0.5 * Y ** 2, N * N)
+        U = np.zeros(N * N)
+        nits, l0 = [], None
+        for s in range(3):
+            F.set_mesh(Q)
+            F.set_prev(U)
+            if l0 is None:
+                l0 = F.context().launches()
+            Unew = jf.newton_krylov(F, U, verbose=0)
+            nits.append((F.last_history["nit"], F.last_history["nfev"], F.last_history["reorth"]))
+            Q = F.relax_mesh(Q, U, min((1 + U) ** 3) * k, loops=1)
+            U = Unew
+        out[fused] = (U, nits, F.context().launches() - l0)
+    assert [n[0] for n in out["1"][1]] == [n[0] for n in out["0"][1]]
+    assert all(abs(a[1] - b[1]) <= 3 for a, b in zip(out["1"][1], out["0"][1]))
+    assert rel(out["1"][0], out["0"][0]) < 3e-9
+    assert out["1"][2] < out["0"][2] / 5
+    if tau > 0.9:
+        assert sum(n[2] for n in out["1"][1]) > 5  # the second Gram-Schmidt pass of the cycle kernel was exercised
