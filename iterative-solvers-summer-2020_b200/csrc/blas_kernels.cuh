@@ -13,16 +13,19 @@ namespace jfnk {
 // NV = accumulators compiled in (nv <= NV at run time), U = double2 elements per thread per sweep: few basis
 // vectors -> several elements per thread so that every thread still keeps >= 8 independent 128-bit loads in flight.
 // (two 256-thread CTAs per SM: <= 128 registers, checked with -Xptxas -v; one CTA/SM starves the memory pipe)
+// nvb > 1: the vector is summed as nvb virtual blocks of n / nvb elements (rank-count-independent sums, cuda_common.cuh)
 template <int NV, int U>
 __global__ void __launch_bounds__(256, 2) mdot_kernel(PtrList V, int nv, const double* __restrict__ w, size_t n,
-                                                      double* S, int out_off, ReduceWs ws, P2PReduceArgs R) {
+                                                      double* S, int out_off, ReduceWs ws, P2PReduceArgs R, int nvb) {
   if (S[JS_STOP] != 0.0) return; // speculatively enqueued Arnoldi step after the process stopped
   double acc[NV + 1];
+  const size_t nb2 = (n / (size_t)nvb) >> 1; // double2 elements per virtual block (the launcher makes it whole when nvb > 1)
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int vb = 0; vb < nvb; ++vb) {
+  const size_t n2 = (size_t)(vb + 1) * nb2; // this block is the index range [vb nb2, n2)
 #pragma unroll
   for (int k = 0; k <= NV; ++k) acc[k] = 0.0;
-  const size_t n2 = n >> 1;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n2; i0 += stride * U) {
+  for (size_t i0 = (size_t)vb * nb2 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n2; i0 += stride * U) {
     double2 wv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(256, 2) mdot_kernel(PtrList V, int nv, const d
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[NV] = fma(wv[u].y, wv[u].y, fma(wv[u].x, wv[u].x, acc[NV]));
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { // odd tail element
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { // odd tail element (only with nvb == 1)
     double we = w[n - 1];
 #pragma unroll
     for (int k = 0; k < NV; ++k)
@@ -58,7 +61,9 @@ __global__ void __launch_bounds__(256, 2) mdot_kernel(PtrList V, int nv, const d
     acc[NV] = fma(we, we, acc[NV]);
   }
   // acc[0..nv) are the dots, acc[NV] is w.w; the reduction writes them contiguously: out[0..nv-1], out[nv]
-  const bool last = grid_reduce_sums<NV + 1>(acc, nv, ws, S + out_off);
+  seg_store<NV + 1>(acc, nv, vb, ws);
+  } // virtual blocks
+  const bool last = seg_finalize(nv + 1, nvb, ws, S + out_off);
   // slab ranks: the finalising CTA all-reduces the nv + 1 sums over peer memory (no separate collective launch)
   if (last && R.nranks > 1) p2p_allreduce_block(R);
 }
@@ -92,7 +97,8 @@ __global__ void __launch_bounds__(256) mdot_scalar_kernel(PtrList V, int nv, con
 // issued back to back), U = double2 elements per thread per sweep.
 template <int MODE, int NV, int U>
 __global__ void __launch_bounds__(256, 2) maxpy_kernel(PtrList V, int nv, double* __restrict__ w, size_t n, double* S,
-                                                       int c_off, int n2_off, int fuse_j, ReduceWs ws, P2PReduceArgs R) {
+                                                       int c_off, int n2_off, int fuse_j, ReduceWs ws, P2PReduceArgs R,
+                                                       int nvb) {
   if (S[JS_STOP] != 0.0) return; // (the host clears JS_STOP before it assembles dx with MODE 2)
   __shared__ double c[JF_MAXV];
   if (threadIdx.x < JF_MAXV) {
@@ -105,9 +111,12 @@ __global__ void __launch_bounds__(256, 2) maxpy_kernel(PtrList V, int nv, double
   }
   __syncthreads();
   double acc[1] = {0.0};
-  const size_t n2 = n >> 1;
+  const size_t nb2 = (n / (size_t)nvb) >> 1; // double2 elements per virtual block (rank-count-independent norm, cuda_common.cuh)
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n2; i0 += stride * U) {
+  for (int vb = 0; vb < nvb; ++vb) {
+  const size_t n2 = (size_t)(vb + 1) * nb2; // this block is the index range [vb nb2, n2)
+  acc[0] = 0.0;
+  for (size_t i0 = (size_t)vb * nb2 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n2; i0 += stride * U) {
     double2 t[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -149,13 +158,15 @@ __global__ void __launch_bounds__(256, 2) maxpy_kernel(PtrList V, int nv, double
       }
     }
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { // odd tail element
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { // odd tail element (only with nvb == 1)
     double tt = (MODE == 2) ? 0.0 : w[n - 1];
     for (int k = 0; k < nv; ++k) tt = fma(c[k], V.p[k][n - 1], tt);
     w[n - 1] = tt;
     acc[0] = fma(tt, tt, acc[0]);
   }
-  const bool last = grid_reduce<1>(acc, 0u, ws, S + n2_off);
+  seg_store<1>(acc, 0, vb, ws);
+  } // virtual blocks
+  const bool last = seg_finalize(1, nvb, ws, S + n2_off);
   // The finalising CTA goes on: with slab ranks it all-reduces the norm over peer memory and then (R.givens_j >= 0) runs
   // the Givens step of the column on the reduced value; on one GPU its thread 0 (which just wrote the norm) runs the
   // Givens step of column fuse_j directly.  Either way an Arnoldi step is operator + multi-dot + this kernel.

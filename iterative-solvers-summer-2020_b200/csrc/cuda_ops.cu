@@ -52,7 +52,7 @@ class CudaOps : public DeviceOps {
     sms_ = sms > 0 ? sms : 148;
     if (!ck(cudaMalloc(&S_, sizeof(double) * JS_COUNT), "cudaMalloc(scalars)")) { why = err_; return; }
     if (!ck(cudaMemsetAsync(S_, 0, sizeof(double) * JS_COUNT, stream_), "cudaMemset(scalars)")) { why = err_; return; }
-    if (!ck(cudaMalloc(&ws_.partials, sizeof(double) * (size_t)kMaxBlocks * kPartialStride), "cudaMalloc(partials)")) { why = err_; return; }
+    if (!ck(cudaMalloc(&ws_.partials, sizeof(double) * (size_t)kMaxVirtualBlocks * kMaxBlocks * kPartialStride), "cudaMalloc(partials)")) { why = err_; return; }
     if (!ck(cudaMalloc(&ws_.ticket, sizeof(unsigned)), "cudaMalloc(ticket)")) { why = err_; return; }
     if (!ck(cudaMemsetAsync(ws_.ticket, 0, sizeof(unsigned), stream_), "cudaMemset(ticket)")) { why = err_; return; }
     if (!ck(cudaMallocHost(&pinned_, sizeof(double) * (JS_COUNT + 1)), "cudaMallocHost")) { why = err_; return; }
@@ -276,13 +276,42 @@ class CudaOps : public DeviceOps {
     return (int)std::max<long long>(1, std::min(cap, need));
   }
 
+  // Rank-count-independent sums (cuda_common.cuh): how many virtual blocks this rank sweeps one after the other -- 8 / P when
+  // the grid splits into 8 blocks of whole rows and a block is large enough to fill the resident grid of `kernel` on its own
+  // (so that the grid, and with it the summation order inside a block, is what an 8-rank run uses); else 1 (plain sums).
+  template <typename K>
+  int virtual_blocks(K kernel, int threads, int elems_per_thread_pass) {
+    const char* env = getenv("JFNK_DET_REDUCE"); // (read per launch: the tests flip it)
+    if (env && atoi(env) == 0) return 1;
+    const int P = g_.nranks;
+    if (!(P == 1 || P == 2 || P == 4 || P == 8) || (g_.ny % kMaxVirtualBlocks) != 0 || g_.nrows * P != g_.ny) return 1;
+    const int nvb = kMaxVirtualBlocks / P;
+    const size_t nb_ = g_.n() / (size_t)nvb;
+    if (nb_ * (size_t)nvb != g_.n() || (nb_ & 1)) return 1;
+    resident_grid(kernel, threads, 1); // (fills the occupancy cache)
+    const long long cap = std::min<long long>((long long)sms_ * occupancy_[reinterpret_cast<const void*>(kernel)], kMaxBlocks);
+    const long long need = (long long)(nb_ / (size_t)elems_per_thread_pass + threads - 1) / threads;
+    return need >= cap ? nvb : 1;
+  }
   template <int NV>
   void mdot_launch(bool vec, const PtrList& L, int nv, const double* w, int out_off, const P2PReduceArgs& R) {
     size_t n = g_.n();
     constexpr int U = NV <= 4 ? 4 : (NV <= 8 ? 2 : 1);
     Prof prof(this, out_off == JS_RD2 ? K_MDOT2 : K_MDOT, nb(nv + 1));
-    if (vec) mdot_kernel<NV, U><<<resident_grid(mdot_kernel<NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, ws_, R);
-    else mdot_scalar_kernel<NV><<<resident_grid(mdot_scalar_kernel<NV>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, ws_, R);
+    if (vec) {
+      const int nvb = virtual_blocks(mdot_kernel<NV, U>, 256, 2 * U);
+      mdot_kernel<NV, U><<<resident_grid(mdot_kernel<NV, U>, 256, n / nvb / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, ws_, R, nvb);
+    } else mdot_scalar_kernel<NV><<<resident_grid(mdot_scalar_kernel<NV>, 256, n), 256, 0, stream_>>>(L, nv, w, n, S_, out_off, ws_, R);
+  }
+  // true when the plain multi-dot of one vector runs in the rank-count-independent mode on this grid
+  bool det_sums() { return virtual_blocks(mdot_kernel<2, 4>, 256, 8) > 1 || (g_.nranks == kMaxVirtualBlocks && det_sums_8()); }
+  bool det_sums_8() { // (8 ranks: one virtual block per rank -- "on" means the same size test passes)
+    const char* env = getenv("JFNK_DET_REDUCE");
+    if (env && atoi(env) == 0) return false;
+    if ((g_.ny % kMaxVirtualBlocks) != 0 || g_.nrows * g_.nranks != g_.ny || (g_.n() & 1)) return false;
+    resident_grid(mdot_kernel<2, 4>, 256, 1);
+    const long long cap = std::min<long long>((long long)sms_ * occupancy_[reinterpret_cast<const void*>(mdot_kernel<2, 4>)], kMaxBlocks);
+    return (long long)(g_.n() / 8 + 255) / 256 >= cap;
   }
   void mdot(int nv, const double* const* V, const double* w, int out_off) override { mdot_any(nv, V, w, out_off, false); }
   // local sums + all-reduce over the slab ranks; with peer memory the finalising CTA of the kernel does the exchange
@@ -342,7 +371,8 @@ class CudaOps : public DeviceOps {
   template <int MODE, int NV, int U>
   void maxpy_vec(const PtrList& L, int nv, double* w, int c_off, int n2_off, int fuse_j, const P2PReduceArgs& R) {
     size_t n = g_.n();
-    maxpy_kernel<MODE, NV, U><<<resident_grid(maxpy_kernel<MODE, NV, U>, 256, n / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, fuse_j, ws_, R);
+    const int nvb = virtual_blocks(maxpy_kernel<MODE, NV, U>, 256, 2 * U);
+    maxpy_kernel<MODE, NV, U><<<resident_grid(maxpy_kernel<MODE, NV, U>, 256, n / nvb / 2 / U), 256, 0, stream_>>>(L, nv, w, n, S_, c_off, n2_off, fuse_j, ws_, R, nvb);
   }
   void gs_update(int nv, const double* const* V, double* w, int rd_off, int n2_off, int fuse_givens_j) override {
     maxpy_launch<0>(nv, V, w, rd_off, n2_off, g_.nranks == 1 ? fuse_givens_j : -1);
@@ -783,6 +813,9 @@ class CudaOps : public DeviceOps {
     } else {
       sh_launch<OP_RESID, false>(A);
     }
+    // The marching kernel cuts its work by slab height, so ITS sum of F^2 depends on the number of ranks; ||F||^2 scales the
+    // start vector of the next cycle, so it is recomputed by the rank-count-independent multi-dot (8 B/point, 7 per step).
+    if (det_sums()) mdot_any(0, nullptr, F, norm_off, false);
   }
   void sh_bind_x0(const double* x0) override {
     const double *t, *b;

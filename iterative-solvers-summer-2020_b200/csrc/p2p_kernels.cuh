@@ -3,7 +3,7 @@
 //   * p2p_halo_kernel     -- halo exchange by direct stores: each rank writes its first / last two rows straight into
 //                            its ring neighbours' halo buffers, then raises their arrival flags and waits for its own;
 //   * p2p_allreduce_kernel -- one-shot all-reduce of <= 64 fp64 scalars: every rank stores its partials into every
-//                            peer's mailbox, raises a flag, waits for all flags and sums the P rows in rank order
+//                            peer's mailbox, raises a flag, waits for all flags and sums the P rows in a fixed pairwise tree
 //                            (identical bits on every rank, so the replicated Hessenberg/Givens state cannot diverge).
 // Both replace an NCCL call (send/recv pair, ncclAllReduce) whose cost at these sizes (256 KiB, <= 50 doubles) is pure
 // launch + protocol latency.  Flags carry monotonically increasing epochs; payload buffers are double-buffered by
@@ -118,11 +118,15 @@ __device__ __forceinline__ void p2p_allreduce_block(const P2PReduceArgs& A) {
   }
   __syncthreads();
   if (i < A.cnt) {
-    double acc = __ldcg(A.my_mailbox + i);
-    for (int r = 1; r < A.nranks; ++r) {
-      const double v = __ldcg(A.my_mailbox + (size_t)r * kP2PMaxScalars + i);
-      acc = A.op ? fmax(acc, v) : acc + v;
-    }
+    // sums: the fixed pairwise tree of the rank-count-independent reductions (cuda_common.cuh), the same bits on every rank
+    double v[kP2PMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kP2PMaxRanks; ++r) v[r] = (r < A.nranks) ? __ldcg(A.my_mailbox + (size_t)r * kP2PMaxScalars + i) : 0.0;
+    double acc;
+    if (A.op) {
+      acc = v[0];
+      for (int r = 1; r < A.nranks; ++r) acc = fmax(acc, v[r]);
+    } else acc = tree_sum(v, A.nranks);
     A.S[A.off + i] = acc;
   }
   if (A.givens_j >= 0) {

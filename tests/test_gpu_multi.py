@@ -79,3 +79,35 @@ def test_nccl_slab_solver_matches_single_gpu_and_oracle(tmp_path, N, variant, p2
     assert list(multi["nit"]) == [len(h["iters"]) for h in href]
     single = jf.SHResidual(N=N, d=0.625 * N).steps(U0, nsteps)
     assert np.linalg.norm(multi["U"] - single) / np.linalg.norm(single) < 1e-8
+
+
+def test_slab_run_is_bitwise_the_single_gpu_run(tmp_path):
+    """Rank-count-independent sums (csrc/cuda_common.cuh): on grids of >= 8 x (a resident grid's worth of) points every
+    global sum is formed as 8 virtual blocks of rows combined in a fixed pairwise tree -- whatever the number of ranks --
+    and everything else on the path is pointwise, so the slab-decomposed run reproduces the single-GPU field BIT FOR BIT
+    (4096^2: 134 MB per vector, one virtual block = 2.1 M points)."""
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    import jfnk_b200 as jf
+
+    N, nsteps = 4096, 2
+    out = str(tmp_path / "out.npz")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, N=N, nsteps=nsteps, out=out, variant=0))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=dict(os.environ))
+    assert r.returncode == 0, r.stdout[-4000:]
+    multi = np.load(out)
+    assert int(multi["peer"]) == 1
+    U0 = jf.seeded_slab_state(N, 0, N, seed=1234)
+    F = jf.SHResidual(N=N, d=0.625 * N)
+    hist = []
+    single = F.steps(U0, nsteps, history=hist)
+    assert list(multi["nit"]) == [h["nit"] for h in hist]
+    assert np.array_equal(multi["U"], single), np.abs(multi["U"] - single).max()
+    assert np.array_equal(multi["Lu"], F.spmv_L(U0))
