@@ -21,5 +21,5 @@ for _ in range(3): F.jvp(v)
 F.profile(True)
 for _ in range(20): F.jvp(v)
 p = F.profile_read()
-m = p["mesh"]
+m = p.get("mesh_march", p.get("mesh"))
 print(os.environ.get("JFNK_MARCH_DEBUG", "0"), "mesh launches", m["launches"], "us/launch", 1e3 * m["ms"] / m["launches"], "GB/s", m["bytes"] / m["ms"] / 1e6)

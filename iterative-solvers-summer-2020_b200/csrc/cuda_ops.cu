@@ -42,7 +42,7 @@ const char* const kClassName[K_COUNT] = {"mdot", "gs_update", "maxpy", "lincomb"
 
 class CudaOps : public DeviceOps {
  public:
-  CudaOps(const jfnk_config& c, std::string& why, bool& ok) : variant_(c.kernel_variant) {
+  CudaOps(const jfnk_config& c, std::string& why, bool& ok) : variant_(c.kernel_variant), problem_(c.problem) {
     g_.nx = c.nx; g_.ny = c.ny; g_.row0 = c.row0; g_.nrows = c.nrows; g_.rank = c.rank; g_.nranks = c.nranks;
     stream_ = (cudaStream_t)c.stream;
     ok = false;
@@ -284,10 +284,13 @@ class CudaOps : public DeviceOps {
     const char* env = getenv("JFNK_DET_REDUCE"); // (read per launch: the tests flip it)
     if (env && atoi(env) == 0) return 1;
     const int P = g_.nranks;
+    // only the problems that run on slabs (the mesh problems are single-GPU), and only where a virtual block is many sweeps
+    // of the resident grid: at 2048^2 eight block reductions per launch cost 20-60 % of a 70 us multi-dot, at >= 4096^2 < 2 %
+    if (problem_ != JFNK_PROBLEM_SH && problem_ != JFNK_PROBLEM_SH_LINEAR) return 1;
     if (!(P == 1 || P == 2 || P == 4 || P == 8) || (g_.ny % kMaxVirtualBlocks) != 0 || g_.nrows * P != g_.ny) return 1;
     const int nvb = kMaxVirtualBlocks / P;
     const size_t nb_ = g_.n() / (size_t)nvb;
-    if (nb_ * (size_t)nvb != g_.n() || (nb_ & 1)) return 1;
+    if (nb_ * (size_t)nvb != g_.n() || (nb_ & 1) || nb_ < kDetMinBlock) return 1;
     resident_grid(kernel, threads, 1); // (fills the occupancy cache)
     const long long cap = std::min<long long>((long long)sms_ * occupancy_[reinterpret_cast<const void*>(kernel)], kMaxBlocks);
     const long long need = (long long)(nb_ / (size_t)elems_per_thread_pass + threads - 1) / threads;
@@ -308,7 +311,8 @@ class CudaOps : public DeviceOps {
   bool det_sums_8() { // (8 ranks: one virtual block per rank -- "on" means the same size test passes)
     const char* env = getenv("JFNK_DET_REDUCE");
     if (env && atoi(env) == 0) return false;
-    if ((g_.ny % kMaxVirtualBlocks) != 0 || g_.nrows * g_.nranks != g_.ny || (g_.n() & 1)) return false;
+    if (problem_ != JFNK_PROBLEM_SH && problem_ != JFNK_PROBLEM_SH_LINEAR) return false;
+    if ((g_.ny % kMaxVirtualBlocks) != 0 || g_.nrows * g_.nranks != g_.ny || (g_.n() & 1) || g_.n() < kDetMinBlock) return false;
     resident_grid(mdot_kernel<2, 4>, 256, 1);
     const long long cap = std::min<long long>((long long)sms_ * occupancy_[reinterpret_cast<const void*>(mdot_kernel<2, 4>)], kMaxBlocks);
     return (long long)(g_.n() / 8 + 255) / 256 >= cap;
@@ -896,7 +900,14 @@ class CudaOps : public DeviceOps {
     const long long target = std::min<long long>((long long)sms_ * per_sm, kMaxBlocks);
     const long long nf = 8LL * g_.nx + 8LL * (g_.ny - 8);
     const int rows = g_.ny - 8;
-    A.nstrips = (g_.nx - 8 + kMarchOut - 1) / kMarchOut;
+    // operand rows by bulk-TMA copies when every field is 16-byte aligned and the rows are an even number of doubles long
+    static const bool tma_off = getenv("JFNK_MARCH_TMA") && atoi(getenv("JFNK_MARCH_TMA")) == 0;
+    bool tma = !tma_off && (g_.nx % 2 == 0) && aligned16(A.x) && (!A.v || aligned16(A.v)) && aligned16(A.out);
+    for (int i = 3; i < 7 && tma; ++i) tma = aligned16(A.M.m[i]);
+    if (MODE != MARCH_LAP) tma = tma && aligned16(A.px) && (!A.pv || aligned16(A.pv)) && aligned16(A.uval) && aligned16(A.cn) && (!A.f0 || aligned16(A.f0));
+    A.tma = tma ? 1 : 0;
+    const int outw = march_out(tma);
+    A.nstrips = (g_.nx - 8 + outw - 1) / outw;
     A.nframe_ctas = (int)std::max<long long>(1, std::min<long long>((nf + kMarchThreads - 1) / kMarchThreads, target / 8));
     long long chunks = std::max<long long>(1, (target - A.nframe_ctas) / A.nstrips);
     A.rows_per_chunk = std::max<int>(kMarchMinRows, (int)((rows + chunks - 1) / chunks));
@@ -1340,8 +1351,10 @@ class CudaOps : public DeviceOps {
     if (code_ == JFNK_OK) { code_ = JFNK_NCCL_ERROR; err_ = std::string(what) + ": " + (nccl_ ? nccl_->GetErrorString(r) : "nccl"); }
   }
 
+  static constexpr size_t kDetMinBlock = (size_t)1 << 21; // points per virtual block from which the sums are rank-count-independent
   Grid g_;
   int variant_;
+  int problem_;
   int device_ = 0, sms_ = 148;
   cudaStream_t stream_ = nullptr;
   double* S_ = nullptr;

@@ -7,8 +7,9 @@
 //   * vertical neighbours live in register windows (7 rows of t, 5 of A22, 5 of g = A12 * D_ksi t), held as circular
 //     buffers whose indices are compile-time constants because the row loop is unrolled by the period (7);
 //   * horizontal neighbours come from an 8-row shared-memory ring of t and 2-row rings of A11 and f = A12 * D_eta t;
-//   * every operand is read from global memory once per point (own column, coalesced) by cp.async into a per-thread
-//     slot of a 4-stage shared-memory ring, three rows ahead of its use (no registers held across the latency);
+//   * every operand is read from global memory once per point: one elected thread issues a bulk-TMA copy of the strip's
+//     row of every field (1 KiB each, completion counted on an mbarrier) into a 4-stage shared-memory ring two rows ahead of
+//     its use; unaligned / odd grids fall back to one 8-byte cp.async per thread and field, one row ahead;
 //   * the stencil input may be the combination t = x + a v (FD-JVP / line search), formed when a row is consumed;
 //   * divisions by 288 h^2, J, dt and the FD step are multiplications by a correctly rounded reciprocal.
 // One block barrier per row.  Only interior points (4 <= r < ny-4, 4 <= c < nx-4: no closure stencil in reach) are
@@ -26,6 +27,7 @@
 #pragma once
 #include "cuda_common.cuh"
 #include "mesh_kernels.cuh"
+#include "sh_kernels.cuh" // mbarrier / bulk-TMA helpers
 
 namespace jfnk {
 
@@ -39,14 +41,23 @@ namespace jfnk {
 #define JFNK_MARCH_MINCTAS 4
 #endif
 constexpr int kMarchThreads = JFNK_MARCH_THREADS;
-constexpr int kMarchHalo = 3;
-constexpr int kMarchOut = kMarchThreads - 2 * kMarchHalo; // output columns per strip
+// halo columns per side / output columns per strip: 3 / 122 with per-thread cp.async operand fetch; 4 / 120 with bulk-TMA
+// row copies, whose source must be 16-byte aligned (strip origins at even columns)
+__host__ __device__ constexpr int march_halo(bool tma) { return tma ? 4 : 3; }
+__host__ __device__ constexpr int march_out(bool tma) { return kMarchThreads - 2 * march_halo(tma); }
 constexpr int kMarchRing = 8;                             // rows of t kept in shared memory (5 live; power of 2)
 constexpr int kMarchPad = 4;                              // slack columns so that halo threads index in range
 constexpr int kMarchMinRows = 8;                          // rows per chunk at least (6 warm-up rows per chunk)
 
-constexpr int kMarchAhead = 3;                            // rows of operands in flight ahead of the row being computed
-constexpr int kMarchStages = kMarchAhead + 1;             // cp.async ring depth
+// Rows of operands in flight ahead of the row being computed.  Measured at 2048^2 (profiles/march_components_r2.txt, us per
+// launch averaged over the two passes of a PMA2 FD-JVP): per-thread cp.async 1 / 3 / 7 rows ahead 81.6 / 94.6 / 95.5 (a deeper
+// cp.async.ca pipeline thrashes what the shared-memory carve-out leaves of L1); bulk TMA 1 / 2 / 3 rows ahead 80.3 / 77.9 / 85.6.
+#ifndef JFNK_MARCH_AHEAD
+#define JFNK_MARCH_AHEAD 2
+#endif
+constexpr int kMarchAhead = JFNK_MARCH_AHEAD;             // bulk-TMA path
+constexpr int kMarchAheadCp = 1;                          // per-thread cp.async path
+constexpr int kMarchStages = kMarchAhead + 2;             // operand ring depth (the cp.async path uses kMarchAheadCp + 1 of them)
 
 enum MarchMode { MARCH_LAP = 0, MARCH_PMA2_RESID = 1, MARCH_PMA2_JVP = 2 };
 // operand fields staged per row by cp.async: stencil input (x, v), A12 and A22 of row r+2, A11 and J of row r, and the
@@ -56,7 +67,7 @@ enum MarchField { MF_X = 0, MF_V = 1, MF_PV = 1, MF_A12N, MF_A22, MF_A11, MF_J, 
 __host__ __device__ constexpr int march_fields(int mode) { return mode == MARCH_LAP ? MF_PX : MF_COUNT; }
 constexpr int kMarchW = kMarchThreads + 2 * kMarchPad;
 __host__ __device__ constexpr size_t march_smem_bytes(int mode) {
-  return sizeof(double) * ((size_t)(kMarchRing + 4) * kMarchW + (size_t)kMarchStages * march_fields(mode) * kMarchThreads);
+  return sizeof(double) * ((size_t)(kMarchRing + 4) * kMarchW + (size_t)kMarchStages * march_fields(mode) * kMarchThreads + kMarchStages);
 }
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
@@ -79,8 +90,11 @@ struct MarchArgs {
   double *out, *out2;
   int norm_off, deriv_bc;
   int rows_per_chunk, nstrips, nframe_ctas;
+  int tma;        // operand rows fetched by one elected thread with bulk-TMA copies (1 KiB per field and row, completion on an
+                  // mbarrier) instead of one 8-byte cp.async per thread and field: needs nx even and 16-byte aligned fields
   int skippable;  // part of a speculatively enqueued Arnoldi step: return at once while JS_STOP is set
-  int debug_skip; // profiling aid (JFNK_MARCH_DEBUG): 1 = frame CTAs idle, 2 = interior CTAs idle; results are then wrong
+  int debug_skip; // profiling aid (JFNK_MARCH_DEBUG): 1 = frame CTAs idle, 2 = interior CTAs idle, 3 = no row barrier,
+                  // 4 = no output phase (staging only), 6 = no operand fetch (compute only); results are then wrong
 };
 
 template <int MODE, bool HAS_V>
@@ -94,6 +108,7 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
   double (*A11s)[W] = Ts + kMarchRing;                                             // [2][W]
   double (*Fs)[W] = A11s + 2;                                                      // [2][W]
   double* Pf = reinterpret_cast<double*>(Fs + 2);                                  // [stage][field][thread]
+  uint64_t* full = reinterpret_cast<uint64_t*>(Pf + (size_t)kMarchStages * NF * kMarchThreads); // [stage], bulk-TMA path
   const MeshGeom& g = A.gm;
   const int nx = g.nx, ny = g.ny;
   const int tid = threadIdx.x;
@@ -163,9 +178,19 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
     const int strip = id % A.nstrips, chunk = id / A.nstrips;
     const int r0 = 4 + chunk * A.rows_per_chunk;
     const int r1 = min(ny - 4, r0 + A.rows_per_chunk);
-    const int c_raw = 4 + strip * kMarchOut - kMarchHalo + tid;
+    const bool tma = A.tma != 0;
+    const int halo = march_halo(tma), outw = march_out(tma);
+    const int c_strip = 4 + strip * outw - halo; // first column of the strip (even with bulk-TMA fetch)
+    const int c_raw = c_strip + tid;
     const int c = min(c_raw, nx - 1); // threads past the right edge load a valid column and compute nothing
-    const bool is_out = tid >= kMarchHalo && tid < kMarchHalo + kMarchOut && c_raw < nx - 4;
+    const bool is_out = tid >= halo && tid < halo + outw && c_raw < nx - 4;
+    if (tma) {
+      if (tid == 0) {
+        for (int i = 0; i < kMarchStages; ++i) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+    }
     const int st = tid + kMarchPad;
     const double* __restrict__ Jp = A.M.m[3];
     const double* __restrict__ A11p = A.M.m[4];
@@ -207,9 +232,37 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
     // of a shared-memory ring by cp.async kMarchAhead rows before they are used -- ~4 us of loads in flight per
     // thread without holding a register, enough to cover HBM latency under load.  A thread only ever reads the slots
     // it filled itself, so completion is tracked with cp.async groups and needs no barrier.
+    // bulk-TMA path: ring of kMarchAhead + 2 stages indexed by the row count -- the stage refilled at the top of iteration r
+    // was last read before the barrier of iteration r-1 (its post-barrier operands J, u, uval, cn, f0 included)
+    const uint32_t row_bytes = (uint32_t)(min(kMarchThreads, nx - c_strip) * 8);
     auto issue = [&](int r) {
-      if (r < r1) {
-        double* pf = Pf + (size_t)(r & (kMarchStages - 1)) * NF * kMarchThreads + tid;
+      if (tma) {
+        if (tid == 0 && r < r1 && A.debug_skip != 6) {
+          const int stg = (r - r0) % kMarchStages;
+          double* pf = Pf + (size_t)stg * NF * kMarchThreads;
+          uint64_t* bar = &full[stg];
+          const size_t o3 = (size_t)(r + 3) * nx + c_strip, o2 = (size_t)(r + 2) * nx + c_strip, o0 = (size_t)r * nx + c_strip;
+          int nf = 5 + (HAS_V ? 1 : 0);
+          if (MODE != MARCH_LAP) nf += 3 + (has_pv ? 1 : 0) + (MODE == MARCH_PMA2_JVP ? 1 : 0);
+          mbar_expect_tx(bar, row_bytes * (uint32_t)nf);
+          tma_load(pf + MF_X * kMarchThreads, A.x + o3, row_bytes, bar);
+          if (HAS_V) tma_load(pf + MF_V * kMarchThreads, A.v + o3, row_bytes, bar);
+          tma_load(pf + MF_A12N * kMarchThreads, A12p + o2, row_bytes, bar);
+          tma_load(pf + MF_A22 * kMarchThreads, A22p + o2, row_bytes, bar);
+          tma_load(pf + MF_A11 * kMarchThreads, A11p + o0, row_bytes, bar);
+          tma_load(pf + MF_J * kMarchThreads, Jp + o0, row_bytes, bar);
+          if (MODE != MARCH_LAP) {
+            tma_load(pf + MF_PX * kMarchThreads, A.px + o0, row_bytes, bar);
+            if (has_pv) tma_load(pf + MF_PV * kMarchThreads, A.pv + o0, row_bytes, bar);
+            tma_load(pf + MF_UVAL * kMarchThreads, A.uval + o0, row_bytes, bar);
+            tma_load(pf + MF_CN * kMarchThreads, A.cn + o0, row_bytes, bar);
+            if (MODE == MARCH_PMA2_JVP) tma_load(pf + MF_F0 * kMarchThreads, A.f0 + o0, row_bytes, bar);
+          }
+        }
+        return;
+      }
+      if (r < r1 && A.debug_skip != 6) {
+        double* pf = Pf + (size_t)((r - r0) % (kMarchAheadCp + 1)) * NF * kMarchThreads + tid;
         const size_t o3 = (size_t)(r + 3) * nx + c, o2 = (size_t)(r + 2) * nx + c, o0 = (size_t)r * nx + c;
         cp_async8(pf + MF_X * kMarchThreads, A.x + o3);
         if (HAS_V) cp_async8(pf + MF_V * kMarchThreads, A.v + o3);
@@ -227,16 +280,19 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
       }
       cp_async_commit(); // (an empty group past the last row keeps the group count uniform)
     };
-#pragma unroll
-    for (int k = 0; k < kMarchAhead; ++k) issue(r0 + k);
+    const int ahead = tma ? kMarchAhead : kMarchAheadCp;
+    for (int k = 0; k < ahead; ++k) issue(r0 + k);
     for (int rb = r0; rb < r1; rb += 7) {
 #pragma unroll
       for (int u = 0; u < 7; ++u) {
         const int r = rb + u;
         if (r >= r1) break;
-        issue(r + kMarchAhead);
-        cp_async_wait<kMarchAhead>(); // the group of row r has landed
-        const double* pf = Pf + (size_t)(r & (kMarchStages - 1)) * NF * kMarchThreads + tid;
+        issue(r + ahead);
+        const int q = r - r0;
+        if (tma) {
+          if (A.debug_skip != 6) mbar_wait(&full[q % kMarchStages], (uint32_t)((q / kMarchStages) & 1)); // row r has landed
+        } else cp_async_wait<kMarchAheadCp>(); // the group of row r has landed
+        const double* pf = Pf + (size_t)(tma ? q % kMarchStages : q % (kMarchAheadCp + 1)) * NF * kMarchThreads + tid;
         const double tnew = HAS_V ? combine(pf[MF_X * kMarchThreads], a, pf[MF_V * kMarchThreads]) : pf[MF_X * kMarchThreads];
         tw[(u + 6) % 7] = tnew;
         a22w[(u + 4) % 7] = pf[MF_A22 * kMarchThreads];
@@ -258,8 +314,8 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
           const double vk = wx0 * T2[-2] + wx1 * T2[-1] + wx3 * T2[1] + wx4 * T2[2];
           GW(2) = a12r2 * vk;
         }
-        __syncthreads();
-        if (is_out) {
+        if (A.debug_skip != 3) __syncthreads();
+        if (is_out && A.debug_skip != 4) {
           const double* T = Ts[r & (kMarchRing - 1)] + st;
           const double* AX = A11s[slot] + st;
           const double* FX = Fs[slot] + st;
