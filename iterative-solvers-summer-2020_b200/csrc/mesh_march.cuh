@@ -237,7 +237,9 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
     const uint32_t row_bytes = (uint32_t)(min(kMarchThreads, nx - c_strip) * 8);
     auto issue = [&](int r) {
       if (tma) {
-        if (tid == 0 && r < r1 && A.debug_skip != 6) {
+        // (the issuing lane rotates over the warps: ~30 instructions per row that would otherwise make warp 0 the last to
+        //  reach every row barrier)
+        if (tid == ((r & (kMarchThreads / 32 - 1)) << 5) && r < r1 && A.debug_skip != 6) {
           const int stg = (r - r0) % kMarchStages;
           double* pf = Pf + (size_t)stg * NF * kMarchThreads;
           uint64_t* bar = &full[stg];
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
           const double vk = wx0 * T2[-2] + wx1 * T2[-1] + wx3 * T2[1] + wx4 * T2[2];
           GW(2) = a12r2 * vk;
         }
-        if (A.debug_skip != 3) __syncthreads();
+        if (A.debug_skip != 3 || tma) __syncthreads(); // (the bulk-TMA ring relies on this barrier for its slot reuse)
         if (is_out && A.debug_skip != 4) {
           const double* T = Ts[r & (kMarchRing - 1)] + st;
           const double* AX = A11s[slot] + st;
