@@ -141,8 +141,10 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
   tick(CP_LOAD);
 
   // the band of z rows [r0-2, r0+rows+2) as operator input: T = x0 + sc z (FD Jacobian) or z (linear operator)
-  auto build_T = [&](const double* zglobal, const double* zband, double sc) {
-    for (int e = tid; e < En; e += kCycThreads) {
+  // (t0, ts: first index and stride of the calling thread -- all 256 threads, or the 224 of warps 1..7 while warp 0 runs the
+  //  Givens step of the previous column)
+  auto build_T = [&](const double* zglobal, const double* zband, double sc, int t0, int ts) {
+    for (int e = t0; e < En; e += ts) {
       double zv;
       if (zglobal) zv = zglobal[egoff[e]];
       else {
@@ -154,9 +156,9 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
     }
   };
   // W = operator(T) on the own band (neighbour sums in the order of sh_point_kernel)
-  auto apply = [&](double* W, double scale) {
+  auto apply = [&](double* W, double scale, int t0, int ts) {
     ShAcc acc = {0.0, 0.0, 0.0};
-    for (int p = tid; p < Pn; p += kCycThreads) {
+    for (int p = t0; p < Pn; p += ts) {
       const int c = pcol[p];
       const int cm1 = c - 1 < 0 ? c - 1 + nx : c - 1, cm2 = c - 2 < 0 ? c - 2 + nx : c - 2;
       const int cp1 = c + 1 >= nx ? c + 1 - nx : c + 1, cp2 = c + 2 >= nx ? c + 2 - nx : c + 2;
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
   int nit = 0, reorth = 0;
   double res = 0.0;
   int flags = 0;
+  bool have_spec = false;
   for (int j = 0; j < m; ++j) {
     // choice of z (_gcrotmk.py:96-105 with prepend_outer_v=True): augmentation vectors, then v0, then the last Arnoldi vector
     const double* zg = nullptr;
@@ -249,14 +252,17 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
     else if (j == k) { zb = V; zi = JS_VN2 + 0; }
     else { zb = V + (size_t)j * A.pitch; zi = JS_VN2 + j; }
     if (tid == 0) znidx[j] = zi;
-    const double zn = sqrt(Ssm[zi]);
     double* W = V + (size_t)(j + 1) * A.pitch;
-    build_T(zg, zb, A.omega / zn);
-    __syncthreads();
-    tick(CP_BUILD);
-    apply(W, OP == OP_JVPG ? 1.0 / A.omega : 1.0 / zn);
-    __syncthreads();
-    tick(CP_APPLY);
+    if (!have_spec) { // (else W was formed while the Givens step of column j-1 ran, see below)
+      const double zn = sqrt(Ssm[zi]);
+      build_T(zg, zb, A.omega / zn, tid, kCycThreads);
+      __syncthreads();
+      tick(CP_BUILD);
+      apply(W, OP == OP_JVPG ? 1.0 / A.omega : 1.0 / zn, tid, kCycThreads);
+      __syncthreads();
+      tick(CP_APPLY);
+    }
+    have_spec = false;
     // classical Gram-Schmidt against V_0..V_j: all dots (and w.w) in one exchange, the update and its norm in another
     dots(j + 2, W, JS_RD);
     tick(CP_DOTS);
@@ -270,10 +276,34 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
       if (tid == 0) Ssm[JS_HN2B] = hn2;
       taken = 1;
     } else if (tid == 0) Ssm[JS_HN2A] = hn2;
-    if (tid == 0) hess_givens_step(Ssm, j, taken, 0, hpre);
+    // The Givens step of column j is one thread's serial work (~2.6 k clocks).  Meanwhile warps 1..7 already apply the operator
+    // to the vector just orthogonalised (step j+1's input when j + 1 > k; its norm is all they need from this step) -- dropped
+    // if column j ends the process or asks for a second Gram-Schmidt pass, exactly like the streaming loop's speculation.
+    const bool spec = (A.gs_mode != JFNK_GS_CGS2) && (j + 1 < m);
+    if (spec) {
+      if (tid == 0) Ssm[JS_VN2 + j + 1] = hn2; // (what the Givens step stores there as well)
+      __syncthreads();
+      if (warp == 0) {
+        if (lane == 0) hess_givens_step(Ssm, j, taken, 0, hpre);
+      } else {
+        const int jn = j + 1;
+        const double* zg1 = nullptr;
+        const double* zb1 = nullptr;
+        int zi1;
+        if (jn < k) { zg1 = A.ov[jn]; zi1 = A.ov_zn2[jn]; }
+        else if (jn == k) { zb1 = V; zi1 = JS_VN2 + 0; }
+        else { zb1 = V + (size_t)jn * A.pitch; zi1 = JS_VN2 + jn; }
+        const double zn1 = sqrt(Ssm[zi1]);
+        build_T(zg1, zb1, A.omega / zn1, tid - 32, kCycThreads - 32);
+        asm volatile("bar.sync 1, %0;" ::"n"(kCycThreads - 32) : "memory");
+        apply(V + (size_t)(jn + 1) * A.pitch, OP == OP_JVPG ? 1.0 / A.omega : 1.0 / zn1, tid - 32, kCycThreads - 32);
+      }
+      have_spec = true;
+    } else if (tid == 0) hess_givens_step(Ssm, j, taken, 0, hpre);
     __syncthreads();
     flags = (int)Ssm[JS_FLAGS];
     if (flags & JF_FLAG_NEED_REORTH) {
+      have_spec = false; // (the second pass changes the vector the operator was applied to)
       // the first pass cancelled more than 1/tau: second pass, then column j again from the saved rotated rhs
       dots(j + 2, W, JS_RD2);
       hn2 = update(j + 1, W);
@@ -328,7 +358,7 @@ __global__ void __launch_bounds__(kCycThreads) sh_cycle_kernel(const __grid_cons
   double tn[3] = {0.0, 0.0, 0.0};
   if (OP == OP_JVPG && A.d != nullptr) {
     // F(x0 - dx): the operand band with halos, the residual with its norms, all-reduced like the dots
-    build_T(nullptr, DX, -1.0);
+    build_T(nullptr, DX, -1.0, tid, kCycThreads);
     __syncthreads();
     ShAcc ra = {0.0, 0.0, 0.0};
     for (int p = tid; p < Pn; p += kCycThreads) {

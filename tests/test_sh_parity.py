@@ -486,3 +486,22 @@ def test_one_launch_cycle_kernel_matches_streaming_path(monkeypatch, N, gs, tau)
         S = jf.SHLinearised(N=N, gs=gs, gs_tau=tau)
         lin[fused] = S.steps(0.1 * U0, nsteps=3)[0]
     assert rel(lin["1"], lin["0"]) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("inner_m,outer_k", [(8, 3), (30, 0), (37, 10)])
+def test_one_launch_cycle_kernel_other_krylov_sizes(monkeypatch, inner_m, outer_k):
+    """The cycle kernel sizes its shared-memory basis from inner_m + outer_k: short restarts (many cycles per Newton step, the
+    augmentation ring wrapping), no augmentation at all, and the largest basis the arena allows (inner_m + outer_k + 1 = 48)."""
+    N = 64
+    U0 = seeded_state(N)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("JFNK_CYCLE_FUSED", fused)
+        F = jf.SHResidual(N=N, inner_m=inner_m, outer_k=outer_k)
+        hist = []
+        U = F.steps(U0, 5, history=hist)
+        out[fused] = (U, [h["nit"] for h in hist], [h["inner_iters"] for h in hist])
+    assert out["1"][1] == out["0"][1]
+    assert all(abs(a - b) <= 3 for a, b in zip(out["1"][2], out["0"][2]))
+    assert rel(out["1"][0], out["0"][0]) < 3e-9
