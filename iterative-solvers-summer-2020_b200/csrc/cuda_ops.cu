@@ -83,12 +83,16 @@ class CudaOps : public DeviceOps {
     if (graph_exec_) { cudaStreamSynchronize(stream_); cudaGraphExecDestroy(graph_exec_); }
     if (cap_stream_) cudaStreamDestroy(cap_stream_);
     if (relax_prof_) {
-      long long h[8] = {0};
+      long long h[16 * 16] = {0};
       cudaStreamSynchronize(stream_);
       cudaMemcpy(h, relax_prof_, sizeof(h), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[jfnk relax prof] clocks: sync1+pullQ=%lld metrics=%lld monitor=%lld sync2+pull+smooth=%lld "
+      fprintf(stderr, "[jfnk relax prof] clocks: sync1+pullQ=%lld metrics=%lld monitor=%lld sync2=%lld pullA=%lld smooth=%lld "
                       "wsum+sync3+rhs+rowDCT=%lld sync4+pull+colDCTs=%lld sync5+pull+rowDCT+update=%lld\n",
-              h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+              h[0], h[1], h[2], h[7], h[8], h[3], h[4], h[5], h[6]);
+      for (int c = 1; c < 16; ++c)
+        if (h[16 * c + 1])
+          fprintf(stderr, "[jfnk relax prof] CTA %2d: sync1+pullQ=%lld metrics=%lld monitor=%lld sync2=%lld pullA=%lld smooth=%lld\n", c,
+                  h[16 * c], h[16 * c + 1], h[16 * c + 2], h[16 * c + 7], h[16 * c + 8], h[16 * c + 3]);
       cudaFree(relax_prof_);
     }
     if (cycle_prof_) { // JFNK_CYCLE_PROF=1: where the one-launch cycle kernel spends its clock cycles
@@ -1113,8 +1117,8 @@ class CudaOps : public DeviceOps {
         at.val.clusterDim.x = band_cluster_; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
         cfg.attrs = &at; cfg.numAttrs = 1;
         if (!relax_prof_ && getenv("JFNK_CYCLE_PROF") && atoi(getenv("JFNK_CYCLE_PROF")) != 0 &&
-            cudaMalloc(&relax_prof_, sizeof(long long) * 8) == cudaSuccess)
-          cudaMemsetAsync(relax_prof_, 0, sizeof(long long) * 8, stream_);
+            cudaMalloc(&relax_prof_, sizeof(long long) * 16 * 16) == cudaSuccess)
+          cudaMemsetAsync(relax_prof_, 0, sizeof(long long) * 16 * 16, stream_);
         A.prof = relax_prof_;
         Prof prof(this, K_MESH, nb(2.0)); // HBM sees Q in and out once; everything else stays in shared memory
         return ck(cudaLaunchKernelEx(&cfg, pma_relax_band_kernel, A), "cudaLaunchKernelEx(pma_relax_band)");

@@ -119,10 +119,10 @@ __global__ void __launch_bounds__(kBandThreads) pma_relax_band_kernel(const __gr
   MeshGeom g = A.gm;
   g.tab = &tabs_s;
   const int nx = g.nx, ny = g.ny;
-  const bool timing = (A.prof != nullptr) && blockIdx.x == 0 && tid == 0;
+  const bool timing = (A.prof != nullptr) && tid == 0; // (every CTA keeps its own row of 16 counters)
   long long tlast = timing ? clock64() : 0;
   auto tick = [&](int phase) {
-    if (timing) { const long long t = clock64(); A.prof[phase] += t - tlast; tlast = t; }
+    if (timing) { const long long t = clock64(); A.prof[blockIdx.x * 16 + phase] += t - tlast; tlast = t; }
   };
   const BandLayout L(nx, ny, C);
   double* Cys = band_smem + L.cy;
@@ -228,9 +228,11 @@ __global__ void __launch_bounds__(kBandThreads) pma_relax_band_kernel(const __gr
     }
     tick(2);
     cl.sync(); // [2]
+    tick(7);
     // smoothing sweeps on a band that shrinks by one row per sweep (ping-pong between AE and BE)
     pull(AE, tabA, nA, Aown);
     __syncthreads();
+    tick(8);
     double* a = AE;
     double* b = BE;
     for (int s = 1; s <= A.pp.smoothing_iters; ++s) {
