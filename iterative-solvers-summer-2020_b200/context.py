@@ -155,6 +155,16 @@ class Context:
         raise_for_status(self.lib, rc)
         self.handle = handle
 
+    def check_stream(self, what):
+        """The engine enqueues on the stream that was current when the context was created; Python code that touches the
+        engine's vectors in between (callback, inner_M) runs on torch's CURRENT stream.  Refuse a mismatch instead of racing."""
+        if hasattr(self.buf, "stream_ptr") and self.cfg.stream is not None:
+            now = self.buf.stream_ptr().value or 0
+            then = self.cfg.stream or 0
+            if now != then:
+                raise RuntimeError(f"{what}: torch's current CUDA stream differs from the stream this context was created on; "
+                                   "create the residual object (or its context) under the stream it is used with")
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.jfnk_destroy(self.handle)

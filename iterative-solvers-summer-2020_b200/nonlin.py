@@ -60,6 +60,8 @@ def newton_krylov(F, xin, iter=None, rdiff=None, method="lgmres", inner_maxiter=
     hist = HistoryBuffer()
 
     n = ctx.n
+    if callback is not None or inner_M is not None:
+        ctx.check_stream("newton_krylov(callback= / inner_M=)")
     ps_c = None
     m_update = getattr(inner_M, "update", None) if inner_M is not None else None
     if inner_M is not None:
