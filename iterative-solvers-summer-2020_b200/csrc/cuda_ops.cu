@@ -285,16 +285,18 @@ class CudaOps : public DeviceOps {
   // (so that the grid, and with it the summation order inside a block, is what an 8-rank run uses); else 1 (plain sums).
   template <typename K>
   int virtual_blocks(K kernel, int threads, int elems_per_thread_pass) {
-    const char* env = getenv("JFNK_DET_REDUCE"); // (read per launch: the tests flip it)
+    const char* env = getenv("JFNK_DET_REDUCE"); // (read per launch: the tests flip it) 0: off, 2: wherever a block fills the grid
     if (env && atoi(env) == 0) return 1;
+    const size_t min_block = (env && atoi(env) == 2) ? 0 : kDetMinBlock;
     const int P = g_.nranks;
     // only the problems that run on slabs (the mesh problems are single-GPU), and only where a virtual block is many sweeps
-    // of the resident grid: at 2048^2 eight block reductions per launch cost 20-60 % of a 70 us multi-dot, at >= 4096^2 < 2 %
+    // of the resident grid: the eight block reductions and loop tails per launch cost 20-60 % of a multi-dot at 2048^2,
+    // 7.5 % of a step at 4096^2, 2.3 % at 8192^2 and < 1 % at 16384^2 (profiles/det_sums_cost_r2.txt)
     if (problem_ != JFNK_PROBLEM_SH && problem_ != JFNK_PROBLEM_SH_LINEAR) return 1;
     if (!(P == 1 || P == 2 || P == 4 || P == 8) || (g_.ny % kMaxVirtualBlocks) != 0 || g_.nrows * P != g_.ny) return 1;
     const int nvb = kMaxVirtualBlocks / P;
     const size_t nb_ = g_.n() / (size_t)nvb;
-    if (nb_ * (size_t)nvb != g_.n() || (nb_ & 1) || nb_ < kDetMinBlock) return 1;
+    if (nb_ * (size_t)nvb != g_.n() || (nb_ & 1) || nb_ < min_block) return 1;
     resident_grid(kernel, threads, 1); // (fills the occupancy cache)
     const long long cap = std::min<long long>((long long)sms_ * occupancy_[reinterpret_cast<const void*>(kernel)], kMaxBlocks);
     const long long need = (long long)(nb_ / (size_t)elems_per_thread_pass + threads - 1) / threads;
@@ -316,7 +318,7 @@ class CudaOps : public DeviceOps {
     const char* env = getenv("JFNK_DET_REDUCE");
     if (env && atoi(env) == 0) return false;
     if (problem_ != JFNK_PROBLEM_SH && problem_ != JFNK_PROBLEM_SH_LINEAR) return false;
-    if ((g_.ny % kMaxVirtualBlocks) != 0 || g_.nrows * g_.nranks != g_.ny || (g_.n() & 1) || g_.n() < kDetMinBlock) return false;
+    if ((g_.ny % kMaxVirtualBlocks) != 0 || g_.nrows * g_.nranks != g_.ny || (g_.n() & 1) || g_.n() < (atoi(env ? env : "1") == 2 ? 0 : kDetMinBlock)) return false;
     resident_grid(mdot_kernel<2, 4>, 256, 1);
     const long long cap = std::min<long long>((long long)sms_ * occupancy_[reinterpret_cast<const void*>(mdot_kernel<2, 4>)], kMaxBlocks);
     return (long long)(g_.n() / 8 + 255) / 256 >= cap;
@@ -1355,7 +1357,7 @@ class CudaOps : public DeviceOps {
     if (code_ == JFNK_OK) { code_ = JFNK_NCCL_ERROR; err_ = std::string(what) + ": " + (nccl_ ? nccl_->GetErrorString(r) : "nccl"); }
   }
 
-  static constexpr size_t kDetMinBlock = (size_t)1 << 21; // points per virtual block from which the sums are rank-count-independent
+  static constexpr size_t kDetMinBlock = (size_t)1 << 23; // points per virtual block from which the sums are rank-count-independent
   Grid g_;
   int variant_;
   int problem_;

@@ -81,11 +81,11 @@ def test_nccl_slab_solver_matches_single_gpu_and_oracle(tmp_path, N, variant, p2
     assert np.linalg.norm(multi["U"] - single) / np.linalg.norm(single) < 1e-8
 
 
-def test_slab_run_is_bitwise_the_single_gpu_run(tmp_path):
+def test_slab_run_is_bitwise_the_single_gpu_run(tmp_path, monkeypatch):
     """Rank-count-independent sums (csrc/cuda_common.cuh): on grids of >= 8 x (a resident grid's worth of) points every
     global sum is formed as 8 virtual blocks of rows combined in a fixed pairwise tree -- whatever the number of ranks --
     and everything else on the path is pointwise, so the slab-decomposed run reproduces the single-GPU field BIT FOR BIT
-    (4096^2: 134 MB per vector, one virtual block = 2.1 M points)."""
+    (here 4096^2: 134 MB per vector, one virtual block = 2.1 M points; bench.py shows the same at 16384^2)."""
     import torch
 
     ngpu = torch.cuda.device_count()
@@ -100,6 +100,9 @@ def test_slab_run_is_bitwise_the_single_gpu_run(tmp_path):
     script.write_text(WORKER.format(root=ROOT, N=N, nsteps=nsteps, out=out, variant=0))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+    # (the mode switches itself on from 8192^2, where it costs 2 % of a step; JFNK_DET_REDUCE=2 asks for it wherever a
+    #  virtual block fills the resident grid, so that the mechanism is checked on a grid of a few seconds)
+    monkeypatch.setenv("JFNK_DET_REDUCE", "2")
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=dict(os.environ))
     assert r.returncode == 0, r.stdout[-4000:]
     multi = np.load(out)
