@@ -23,8 +23,9 @@ else:
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 F = jf.DropletResidual(Nx=91, Ny=61)                      # droplet.py:23-53
 scale, t = 1.0, 0.0
-t0 = time.perf_counter()
 for s in range(steps):
+    if s == 1:
+        t0 = time.perf_counter()                          # (the first step pays for CUDA start-up and the context)
     dt_n = 1e-4 * scale                                   # :371
     F.set_mesh(Q)                                         # compute_Q_spatial_ders ; J (:373-376)
     F.set_prev(U, dt_n)                                   # U.val ; P ; F = pde_rhs (:377-381)
@@ -33,4 +34,4 @@ for s in range(steps):
     scale += np.exp(-10 * np.linalg.norm(Unew - U))       # :411
     U = Unew
     t += dt_n
-print(f"{steps} steps: {1e3 * (time.perf_counter() - t0) / steps:.2f} ms/step, t = {t:.4e}, max(U) = {U.max():.6f}, scale = {scale:.4f}")
+print(f"{steps} steps: {1e3 * (time.perf_counter() - t0) / (steps - 1):.2f} ms/step, t = {t:.4e}, max(U) = {U.max():.6f}, scale = {scale:.4f}")
