@@ -305,6 +305,30 @@ class PMA2Residual(_MeshResidual):
         return self
 
 
+def _pma2_run(self, U, Q, nsteps, k=None, history=None, **nk):
+    """The while-loop body of PMA2_nk.py:80-106, ``nsteps`` times: metrics, Crank-Nicolson term, ``newton_krylov``,
+    ``solve_PMA()`` with the old solution and ``Q.val += dt*Q.dt`` with the script's local ``dt = compute_g()*k``.
+    Returns ``(U, Q, t)``."""
+    from .nonlin import newton_krylov
+
+    k = self.dt if k is None else float(k)
+    t = 0.0
+    for _ in range(int(nsteps)):
+        self.set_mesh(Q)
+        self.set_prev(U)
+        g = float(((1 + U) ** 3).min()) if self.epsilon == 0 else 1.0  # compute_g (:446-450)
+        Unew = newton_krylov(self, U, verbose=0, **nk)
+        Q = self.relax_mesh(Q, U, g * k, loops=1)
+        U = Unew
+        t += g * k
+        if history is not None:
+            history.append(dict(self.last_history, t=t))
+    return U, Q, t
+
+
+PMA2Residual.run = _pma2_run
+
+
 class DropletResidual(_MeshResidual):
     """Residual of droplet.py:435-450 on the Nx x Ny moving mesh (defaults: droplet.py:23-53)."""
 
@@ -336,6 +360,32 @@ class DropletResidual(_MeshResidual):
         ctx.check(ctx.lib.jfnk_droplet_set_prev(ctx.handle, ctx.buf.ptr(self._prev), self._dt))
         return self
 
+
+    def evolve_with_PDE(self, U, Q, dt=1e-4, iterMax=101, dtmesh=3e-9, pmaloops=400, scale=1.0, history=None, **nk):
+        """The time loop of droplet.py:360-411 (``evolve_with_PDE(dt, iterMax, dtU, dtmesh, pmaloops)``): ``iterMax - 1``
+        steps of ``dt_n = dt*scale`` -- metrics of the mesh, per-step precompute, ``newton_krylov(..., maxiter=20,
+        f_tol=1e-7)``, ``loop_pma(dtmesh, pmaloops)`` with the OLD solution, ``scale += exp(-10 |dU|)``.  Returns
+        ``(U, Q, t, scale)``; ``history`` (a list) receives one dict per step."""
+        from .nonlin import newton_krylov
+
+        nk.setdefault("maxiter", 20)
+        nk.setdefault("f_tol", 1e-7)
+        t = 0.0
+        for _ in range(1, int(iterMax)):
+            dt_n = dt * scale
+            self.set_mesh(Q)
+            self.set_prev(U, dt_n)
+            Unew = newton_krylov(self, U, verbose=0, **nk)
+            if pmaloops:
+                Q = self.relax_mesh(Q, U, dtmesh, loops=pmaloops)
+            diff = Unew - U
+            nrm = float(diff.norm()) if hasattr(diff, "norm") else float(np.linalg.norm(diff))
+            scale += float(np.exp(-10.0 * nrm))
+            U = Unew
+            t += dt_n
+            if history is not None:
+                history.append(dict(self.last_history, t=t, dt=dt_n, scale=scale))
+        return U, Q, t, scale
 
     # ---- initial states (droplet.py:132-248, :316-358, :413-429, :544-554) --------------------------------------
     def uniform_mesh_potential(self):

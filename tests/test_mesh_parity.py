@@ -474,3 +474,32 @@ def test_one_launch_pma2_cycle_matches_streaming_path(monkeypatch, gs, tau):
     assert out["1"][2] < out["0"][2] / 5
     if tau > 0.9:
         assert sum(n[2] for n in out["1"][1]) > 5  # the second Gram-Schmidt pass of the cycle kernel was exercised
+
+
+def test_time_loop_drivers_match_the_oracle_loops(buffers):
+    """``DropletResidual.evolve_with_PDE`` (droplet.py:360-411) and ``PMA2Residual.run`` (PMA2_nk.py:80-106): the scripts' own
+    time loops as one call, against the oracle stepping the same loops."""
+    g = np.load(os.path.join(GOLD, "droplet_91x61.npz"))
+    F = jf.DropletResidual(buffers=buffers)
+    hist = []
+    U, Q, t, scale = F.evolve_with_PDE(g["state_U"], g["state_Q"], dt=1e-4, iterMax=3, dtmesh=3e-9, pmaloops=20, history=hist)
+    o = DropletOracle()
+    o.Q = g["state_Q"].copy()
+    Ur, sc, tr = g["state_U"].copy(), 1.0, 0.0
+    for _ in range(2):
+        Un = o.step(Ur, 1e-4 * sc, dtmesh=3e-9, pmaloops=20)
+        tr += 1e-4 * sc
+        sc += np.exp(-10 * np.linalg.norm(Un - Ur))
+        Ur = Un
+    assert len(hist) == 2 and abs(t - tr) < 1e-12 and abs(scale - sc) < 1e-7  # (scale feeds on |dU|, known to 1e-8)
+    assert rel(U, Ur) < 1e-8 and rel(Q, o.Q) < 1e-10
+    N = 51
+    P = jf.PMA2Residual(N=N, buffers=buffers)
+    xi = np.linspace(-1, 1, N)
+    X, Y = np.meshgrid(xi, xi)
+    U2, Q2, t2 = P.run(np.zeros(N * N), np.reshape(0.5 * X ** 2 + 0.5 * Y ** 2, N * N), 2)
+    po = PMA2Oracle(N=N)
+    Up = np.zeros(N * N)
+    for _ in range(2):
+        Up = po.step(Up)
+    assert rel(U2, Up) < 1e-8 and rel(Q2, po.Q) < 1e-12
