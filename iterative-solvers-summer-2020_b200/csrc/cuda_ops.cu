@@ -331,6 +331,15 @@ class CudaOps : public DeviceOps {
     mdot_any(nv, V, w, out_off, false);
     allreduce_sum(out_off, nv + 1);
   }
+  // out = sum coef_i Z_i with ||out||^2 all-reduced by the finalising CTA (slab ranks with peer memory)
+  void maxpy_reduced(int nz, const double* const* Z, double* out, int n2_off) override {
+    if (g_.nranks > 1 && fused_reduce(1)) { maxpy_launch<2>(nz, Z, out, JS_COEF, n2_off, -1, p2p_next_reduce(n2_off, 1, 0, -1, 0, 0, 0)); return; }
+    maxpy(nz, Z, out, n2_off);
+    allreduce_sum(n2_off, 1);
+  }
+  // with slab ranks, peer memory and the rank-count-independent sums the residual pass ends with a multi-dot whose finalising
+  // CTA all-reduces all three norms (sum, max, max) in one exchange: no collective launch of its own
+  bool residual_norms_global() override { return g_.nranks > 1 && fused_reduce(3) && det_sums(); }
   void mdot_any(int nv, const double* const* V, const double* w, int out_off, bool reduce) {
     if (nv > 32) {
       // more than 32 accumulators per thread would drop to one CTA per SM: two passes of <= 24 vectors instead
@@ -825,7 +834,14 @@ class CudaOps : public DeviceOps {
     }
     // The marching kernel cuts its work by slab height, so ITS sum of F^2 depends on the number of ranks; ||F||^2 scales the
     // start vector of the next cycle, so it is recomputed by the rank-count-independent multi-dot (8 B/point, 7 per step).
-    if (det_sums()) mdot_any(0, nullptr, F, norm_off, false);
+    if (det_sums()) {
+      if (residual_norms_global()) {
+        // (entry 0: the fresh sum of F^2 ; entries 1, 2: max|F|, max|t| the stencil kernel has just written)
+        PtrList L;
+        for (int i = 0; i < JF_MAXV; ++i) L.p[i] = nullptr;
+        mdot_launch<2>(aligned16(F), L, 0, F, norm_off, p2p_next_reduce(norm_off, 3, 2, -1, 0, 0, 0));
+      } else mdot_any(0, nullptr, F, norm_off, false);
+    }
   }
   void sh_bind_x0(const double* x0) override {
     const double *t, *b;

@@ -154,6 +154,20 @@ class DeviceOps {
   // launch, when the backend has such a kernel for this grid (small single-rank Swift-Hohenberg grids); false = not done.
   virtual bool cycle_fused(const FusedCycleIn& /*in*/, FusedCycleOut& /*out*/) { return false; }
 
+  // S[norm_off..+2] = {sum F^2, max|F|, max|t|} of a residual pass, combined over the slab ranks (sum, max, max).  A backend
+  // whose sh_residual already did that inside its kernels returns true from residual_norms_global().
+  virtual bool residual_norms_global() { return false; }
+  virtual void reduce_residual_norms(int norm_off) {
+    if (residual_norms_global()) return;
+    allreduce_sum(norm_off, 1);
+    allreduce_max(norm_off + 1, 2);
+  }
+  // out = sum_i S[JS_COEF+i] Z_i ; S[n2_off] = ||out||^2 summed over the slab ranks
+  virtual void maxpy_reduced(int nz, const double* const* Z, double* out, int n2_off) {
+    maxpy(nz, Z, out, n2_off);
+    allreduce_sum(n2_off, 1);
+  }
+
   // ---- BLAS-1 on slab-local vectors of length grid.n() -------------------------------------------
   // out[i] = V_i . w (i < nv), out[nv] = w . w
   virtual void mdot(int nv, const double* const* V, const double* w, int out_off) = 0;

@@ -329,8 +329,7 @@ int Engine::eval_residual(const double* x, const double* v, ScalarRef a, double*
     ops_->droplet_eval(mp_, dp_, MF_, x, v, a, UVAL_, CN_, nullptr, sref(1.0), scratch_.data(), v ? xt_out : nullptr, F,
                        norm_off);
   }
-  ops_->allreduce_sum(norm_off, 1);
-  ops_->allreduce_max(norm_off + 1, 2);
+  ops_->reduce_residual_norms(norm_off);
   ops_->read_scalars(norm_off, 3, nrm);
   nfev_++;
   return ops_->status();
@@ -583,8 +582,7 @@ int Engine::cycle(const double* v0vec, double v0n2, double ptol, CycleOut& out) 
   (void)single;
   // y = lstsq(R, Q[0,:]) * inner_res_0 ; dx = sum zs_i y_i (lgmres.py:188,206-208)
   ops_->lsq(nit, znidx, JS_VN2 + 0);
-  ops_->maxpy(nit, zs, OV_[slot], JS_ZN2 + slot);
-  ops_->allreduce_sum(JS_ZN2 + slot, 1);
+  ops_->maxpy_reduced(nit, zs, OV_[slot], JS_ZN2 + slot);
   ops_->read_scalars(JS_ZN2 + slot, 1, &dxn2);
   } // !fused
   out.sol = OV_[slot];

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) p2p_halo_kernel(P2PHaloArgs A) {
 
 struct P2PReduceArgs {
   double* S;                 // local scalar arena: S[off .. off+cnt) reduced in place
-  int off, cnt, op;          // op 0: sum, 1: max
+  int off, cnt, op;          // op 0: sum, 1: max, 2: entry 0 sum and the others max (the three norms of a residual pass)
   int rank, nranks;
   double* mailbox_peer[kP2PMaxRanks];             // peer q's mailbox of this parity: row `rank` is mine to write
   unsigned long long* flags_peer[kP2PMaxRanks];   // peer q's arrival flags: entry `rank` is mine to raise
@@ -123,7 +123,7 @@ __device__ __forceinline__ void p2p_allreduce_block(const P2PReduceArgs& A) {
 #pragma unroll
     for (int r = 0; r < kP2PMaxRanks; ++r) v[r] = (r < A.nranks) ? __ldcg(A.my_mailbox + (size_t)r * kP2PMaxScalars + i) : 0.0;
     double acc;
-    if (A.op) {
+    if (A.op == 1 || (A.op == 2 && i > 0)) {
       acc = v[0];
       for (int r = 1; r < A.nranks; ++r) acc = fmax(acc, v[r]);
     } else acc = tree_sum(v, A.nranks);
