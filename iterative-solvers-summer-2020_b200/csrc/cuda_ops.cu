@@ -930,7 +930,10 @@ class CudaOps : public DeviceOps {
     A.tma = tma ? 1 : 0;
     const int outw = march_out(tma);
     A.nstrips = (g_.nx - 8 + outw - 1) / outw;
-    A.nframe_ctas = (int)std::max<long long>(1, std::min<long long>((nf + kMarchThreads - 1) / kMarchThreads, target / 8));
+    // (share of the resident CTAs given to the frame: its points cost ~10x an interior point, but a slot it holds idles once
+    //  the frame is done -- JFNK_MARCH_FRAME_DIV to measure)
+    static const int frame_div = getenv("JFNK_MARCH_FRAME_DIV") ? std::max(1, atoi(getenv("JFNK_MARCH_FRAME_DIV"))) : 8;
+    A.nframe_ctas = (int)std::max<long long>(1, std::min<long long>((nf + kMarchThreads - 1) / kMarchThreads, target / frame_div));
     long long chunks = std::max<long long>(1, (target - A.nframe_ctas) / A.nstrips);
     A.rows_per_chunk = std::max<int>(kMarchMinRows, (int)((rows + chunks - 1) / chunks));
     const int nchunks = (rows + A.rows_per_chunk - 1) / A.rows_per_chunk;

@@ -52,12 +52,27 @@ constexpr int kMarchMinRows = 8;                          // rows per chunk at l
 // Rows of operands in flight ahead of the row being computed.  Measured at 2048^2 (profiles/march_components_r2.txt, us per
 // launch averaged over the two passes of a PMA2 FD-JVP): per-thread cp.async 1 / 3 / 7 rows ahead 81.6 / 94.6 / 95.5 (a deeper
 // cp.async.ca pipeline thrashes what the shared-memory carve-out leaves of L1); bulk TMA 1 / 2 / 3 rows ahead 80.3 / 77.9 / 85.6.
+// Round 2, late issue (JFNK_MARCH_LATE, ring of ahead + 1 stages): 3 rows ahead in the shared memory 2 rows used to take, with the
+// marching-direction fluxes shared between rows: 79.4 -> 76.3 (profiles/march_components_r2.txt, last block).
 #ifndef JFNK_MARCH_AHEAD
-#define JFNK_MARCH_AHEAD 2
+#define JFNK_MARCH_AHEAD 3
+#endif
+// JFNK_MARCH_LATE: the elected thread issues the copies of row r + ahead AFTER the row barrier of iteration r instead of
+// at its top.  Every thread has then finished iteration r-1 (post-barrier operands included), so the stage of row r-1 can
+// be refilled and the ring needs ahead + 1 stages instead of ahead + 2: one more row in flight in the same shared memory.
+#ifndef JFNK_MARCH_LATE
+#define JFNK_MARCH_LATE 1
+#endif
+// JFNK_MARCH_YSHARE: the half-point fluxes of the conservative formula in the marching direction are computed once per row
+// and carried in registers (P(r+1), H(r+1/2) are new per iteration; P(r-1), P(r), H(r-1/2) come from the two iterations
+// before) instead of being recomputed by the two rows that share them: -13 of ~95 fp64 operations per point.
+#ifndef JFNK_MARCH_YSHARE
+#define JFNK_MARCH_YSHARE 1
 #endif
 constexpr int kMarchAhead = JFNK_MARCH_AHEAD;             // bulk-TMA path
 constexpr int kMarchAheadCp = 1;                          // per-thread cp.async path
-constexpr int kMarchStages = kMarchAhead + 2;             // operand ring depth (the cp.async path uses kMarchAheadCp + 1 of them)
+constexpr int kMarchStages = kMarchAhead + (JFNK_MARCH_LATE ? 1 : 2); // operand ring depth (the cp.async path uses kMarchAheadCp + 1 of them)
+static_assert(kMarchStages >= kMarchAheadCp + 1, "the cp.async path needs two stages");
 
 enum MarchMode { MARCH_LAP = 0, MARCH_PMA2_RESID = 1, MARCH_PMA2_JVP = 2 };
 // operand fields staged per row by cp.async: stencil input (x, v), A12 and A22 of row r+2, A11 and J of row r, and the
@@ -209,31 +224,13 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
     const double rx = __drcp_rn(288 * g.dksi2), ry = __drcp_rn(288 * g.deta2); // one rounding each, instead of a
                                                                               // division per point and direction
 
-    // warm-up: rows r0-3 .. r0+2 of t ; g and A22 of rows r0-2 .. r0+1
-#pragma unroll
-    for (int m = 0; m < 6; ++m) {
-      const int rho = r0 - 3 + m;
-      const size_t off = (size_t)rho * nx + c;
-      double tv = __ldg(A.x + off);
-      if (HAS_V) tv = combine(tv, a, __ldg(A.v + off));
-      tw[m] = tv;
-      Ts[rho & (kMarchRing - 1)][st] = tv;
-      __syncthreads();
-      if (m >= 1 && m <= 4) {
-        const double* T = Ts[rho & (kMarchRing - 1)] + st;
-        const double vk = wx0 * T[-2] + wx1 * T[-1] + wx3 * T[1] + wx4 * T[2];
-        a12_1 = a12_2; a12_2 = __ldg(A12p + off); // ends with A12 of rows r0, r0+1
-        gw[m - 1] = a12_2 * vk;
-        a22w[m - 1] = __ldg(A22p + off);
-      }
-    }
-
     // Operand pipeline: the global operands of row r (own column of every field) are copied into a per-thread slot
     // of a shared-memory ring by cp.async kMarchAhead rows before they are used -- ~4 us of loads in flight per
     // thread without holding a register, enough to cover HBM latency under load.  A thread only ever reads the slots
     // it filled itself, so completion is tracked with cp.async groups and needs no barrier.
-    // bulk-TMA path: ring of kMarchAhead + 2 stages indexed by the row count -- the stage refilled at the top of iteration r
-    // was last read before the barrier of iteration r-1 (its post-barrier operands J, u, uval, cn, f0 included)
+    // bulk-TMA path: ring of kMarchStages stages indexed by the row count.  Issued at the top of iteration r (ahead + 2 stages),
+    // the refilled stage was last read before the barrier of iteration r-1 (its post-barrier operands J, u, uval, cn, f0
+    // included); issued after the barrier of iteration r (JFNK_MARCH_LATE, ahead + 1 stages) it is the stage of row r-1.
     const uint32_t row_bytes = (uint32_t)(min(kMarchThreads, nx - c_strip) * 8);
     auto issue = [&](int r) {
       if (tma) {
@@ -283,13 +280,48 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
       cp_async_commit(); // (an empty group past the last row keeps the group count uniform)
     };
     const int ahead = tma ? kMarchAhead : kMarchAheadCp;
-    for (int k = 0; k < ahead; ++k) issue(r0 + k);
+    for (int k = 0; k < ahead; ++k) issue(r0 + k); // (before the warm-up, so that the first rows land behind it)
+
+    // warm-up: rows r0-3 .. r0+2 of t ; g and A22 of rows r0-2 .. r0+1.  All global loads are issued before the first use and
+    // the six rows go into the ring behind ONE barrier (a load -> store -> barrier chain per row cost six serial memory
+    // latencies per chunk of ~60 rows).
+    {
+      double wa12[4];
+#pragma unroll
+      for (int m = 0; m < 6; ++m) {
+        const size_t off = (size_t)(r0 - 3 + m) * nx + c;
+        double tv = __ldg(A.x + off);
+        if (HAS_V) tv = combine(tv, a, __ldg(A.v + off));
+        tw[m] = tv;
+        if (m >= 1 && m <= 4) {
+          wa12[m - 1] = __ldg(A12p + off);
+          a22w[m - 1] = __ldg(A22p + off);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 6; ++m) Ts[(r0 - 3 + m) & (kMarchRing - 1)][st] = tw[m];
+      __syncthreads();
+#pragma unroll
+      for (int m = 1; m <= 4; ++m) {
+        const double* T = Ts[(r0 - 3 + m) & (kMarchRing - 1)] + st;
+        const double vk = wx0 * T[-2] + wx1 * T[-1] + wx3 * T[1] + wx4 * T[2];
+        gw[m - 1] = wa12[m - 1] * vk;
+      }
+      a12_1 = wa12[2]; a12_2 = wa12[3]; // A12 of rows r0, r0+1
+    }
+
+#if JFNK_MARCH_YSHARE
+    // fluxes of the marching direction carried between rows: P(r0-1), P(r0), H(r0-1/2) from the warm-up rows
+    double py_m1 = a22w[1] * (tw[0] - 8 * tw[1] + 8 * tw[3] - tw[4]);
+    double py_0 = a22w[2] * (tw[1] - 8 * tw[2] + 8 * tw[4] - tw[5]);
+    double hy_m = (-a22w[0] + 9 * a22w[1] + 9 * a22w[2] - a22w[3]) * (tw[1] - 27 * tw[2] + 27 * tw[3] - tw[4]);
+#endif
     for (int rb = r0; rb < r1; rb += 7) {
 #pragma unroll
       for (int u = 0; u < 7; ++u) {
         const int r = rb + u;
         if (r >= r1) break;
-        issue(r + ahead);
+        if (!JFNK_MARCH_LATE || !tma) issue(r + ahead);
         const int q = r - r0;
         if (tma) {
           if (A.debug_skip != 6) mbar_wait(&full[q % kMarchStages], (uint32_t)((q / kMarchStages) & 1)); // row r has landed
@@ -317,6 +349,7 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
           GW(2) = a12r2 * vk;
         }
         if (A.debug_skip != 3 || tma) __syncthreads(); // (the bulk-TMA ring relies on this barrier for its slot reuse)
+        if (JFNK_MARCH_LATE && tma) issue(r + ahead);  // refills the stage of row r-1: every thread is past iteration r-1
         if (is_out && A.debug_skip != 4) {
           const double* T = Ts[r & (kMarchRing - 1)] + st;
           const double* AX = A11s[slot] + st;
@@ -325,10 +358,17 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
                              (-AX[-2] + 9 * AX[-1] + 9 * AX[0] - AX[1]) * (T[-2] - 27 * T[-1] + 27 * T[0] - T[1]) +
                              (-AX[-1] + 9 * AX[0] + 9 * AX[1] - AX[2]) * (T[-1] - 27 * T[0] + 27 * T[1] - T[2]) -
                              4 * (AX[1] * (T[-1] - 8 * T[0] + 8 * T[2] - T[3]))) * rx;
+#if JFNK_MARCH_YSHARE
+          const double pnew = AY(1) * (TW(-1) - 8 * TW(0) + 8 * TW(2) - TW(3));                                          // P(r+1)
+          const double hnew = (-AY(-1) + 9 * AY(0) + 9 * AY(1) - AY(2)) * (TW(-1) - 27 * TW(0) + 27 * TW(1) - TW(2));   // H(r+1/2)
+          const double yy = (4 * py_m1 - hy_m + hnew - 4 * pnew) * ry;
+          py_m1 = py_0; py_0 = pnew; hy_m = hnew;
+#else
           const double yy = (4 * (AY(-1) * (TW(-3) - 8 * TW(-2) + 8 * TW(0) - TW(1))) -
                              (-AY(-2) + 9 * AY(-1) + 9 * AY(0) - AY(1)) * (TW(-2) - 27 * TW(-1) + 27 * TW(0) - TW(1)) +
                              (-AY(-1) + 9 * AY(0) + 9 * AY(1) - AY(2)) * (TW(-1) - 27 * TW(0) + 27 * TW(1) - TW(2)) -
                              4 * (AY(1) * (TW(-1) - 8 * TW(0) + 8 * TW(2) - TW(3)))) * ry;
+#endif
           double accx = 0.0, accy = 0.0;
           accx += wx0 * FX[-2]; accx += wx1 * FX[-1]; accx += wx3 * FX[1]; accx += wx4 * FX[2];
           accy += wy0 * GW(-2); accy += wy1 * GW(-1); accy += wy3 * GW(1); accy += wy4 * GW(2);
