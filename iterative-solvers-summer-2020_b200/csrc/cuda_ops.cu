@@ -909,26 +909,31 @@ class CudaOps : public DeviceOps {
   template <int MODE, bool HAS_V>
   void march_launch(MarchArgs& A, const MeshParams& mp, double vecs) {
     A.gm = geom(mp);
-    constexpr size_t smem = march_smem_bytes(MODE);
-    int& per_sm = occupancy_[reinterpret_cast<const void*>(mesh_march_kernel<MODE, HAS_V>)];
-    if (per_sm == 0) {
-      ck(cudaFuncSetAttribute(mesh_march_kernel<MODE, HAS_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-         "cudaFuncSetAttribute(march smem)");
-      int nb_ = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, mesh_march_kernel<MODE, HAS_V>, kMarchThreads, smem) != cudaSuccess || nb_ < 1) nb_ = 1;
-      per_sm = nb_;
-    }
-    // all CTAs resident at once: a few frame CTAs (general per-point path) + strips x row chunks of the interior
-    const long long target = std::min<long long>((long long)sms_ * per_sm, kMaxBlocks);
-    const long long nf = 8LL * g_.nx + 8LL * (g_.ny - 8);
-    const int rows = g_.ny - 8;
     // operand rows by bulk-TMA copies when every field is 16-byte aligned and the rows are an even number of doubles long
     static const bool tma_off = getenv("JFNK_MARCH_TMA") && atoi(getenv("JFNK_MARCH_TMA")) == 0;
     bool tma = !tma_off && (g_.nx % 2 == 0) && aligned16(A.x) && (!A.v || aligned16(A.v)) && aligned16(A.out);
     for (int i = 3; i < 7 && tma; ++i) tma = aligned16(A.M.m[i]);
     if (MODE != MARCH_LAP) tma = tma && aligned16(A.px) && (!A.pv || aligned16(A.pv)) && aligned16(A.uval) && aligned16(A.cn) && (!A.f0 || aligned16(A.f0));
     A.tma = tma ? 1 : 0;
-    const int outw = march_out(tma);
+    if (tma) march_launch_t<MODE, HAS_V, true>(A, vecs);
+    else march_launch_t<MODE, HAS_V, false>(A, vecs);
+  }
+  template <int MODE, bool HAS_V, bool TMA>
+  void march_launch_t(MarchArgs& A, double vecs) {
+    constexpr size_t smem = march_smem_bytes(MODE);
+    int& per_sm = occupancy_[reinterpret_cast<const void*>(mesh_march_kernel<MODE, HAS_V, TMA>)];
+    if (per_sm == 0) {
+      ck(cudaFuncSetAttribute(mesh_march_kernel<MODE, HAS_V, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+         "cudaFuncSetAttribute(march smem)");
+      int nb_ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, mesh_march_kernel<MODE, HAS_V, TMA>, kMarchThreads, smem) != cudaSuccess || nb_ < 1) nb_ = 1;
+      per_sm = nb_;
+    }
+    // all CTAs resident at once: a few frame CTAs (general per-point path) + strips x row chunks of the interior
+    const long long target = std::min<long long>((long long)sms_ * per_sm, kMaxBlocks);
+    const long long nf = 8LL * g_.nx + 8LL * (g_.ny - 8);
+    const int rows = g_.ny - 8;
+    const int outw = march_out(TMA);
     A.nstrips = (g_.nx - 8 + outw - 1) / outw;
     // (share of the resident CTAs given to the frame: its points cost ~10x an interior point, but a slot it holds idles once
     //  the frame is done -- JFNK_MARCH_FRAME_DIV to measure)
@@ -940,7 +945,7 @@ class CudaOps : public DeviceOps {
     static const int dbg = getenv("JFNK_MARCH_DEBUG") ? atoi(getenv("JFNK_MARCH_DEBUG")) : 0;
     A.debug_skip = (MODE == MARCH_PMA2_RESID) ? 0 : dbg; // (the reduction of RESID needs every CTA)
     Prof prof(this, K_MARCH, nb(vecs));
-    mesh_march_kernel<MODE, HAS_V><<<A.nframe_ctas + A.nstrips * nchunks, kMarchThreads, smem, stream_>>>(A, S_, ws_);
+    mesh_march_kernel<MODE, HAS_V, TMA><<<A.nframe_ctas + A.nstrips * nchunks, kMarchThreads, smem, stream_>>>(A, S_, ws_);
   }
   MarchArgs march_args(const double* const* M, const double* x, const double* v, ScalarRef a, double* out) {
     MarchArgs A;

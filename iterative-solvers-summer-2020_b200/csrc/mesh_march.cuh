@@ -4,8 +4,10 @@
 // The one-thread-per-point kernels of mesh_kernels.cuh fetch every stencil leg from L1/L2 (~60 loads and ~420
 // instructions per point) and are instruction-issue bound at 2048^2.  Here a CTA owns a strip of 122 interior
 // columns (+3 halo columns per side = 128 threads, one column per thread) and marches down a chunk of rows:
-//   * vertical neighbours live in register windows (7 rows of t, 5 of A22, 5 of g = A12 * D_ksi t), held as circular
-//     buffers whose indices are compile-time constants because the row loop is unrolled by the period (7);
+//   * vertical neighbours live in register windows (rows of t, A22 and g = A12 * D_ksi t), held as circular buffers whose
+//     indices are compile-time constants because the row loop is unrolled by the period (8); the shared-memory rings
+//     (8 rows of t, 4 operand stages, 2 rows of A11 and f) are indexed by the row count RELATIVE to the chunk, so their
+//     addresses are immediates too (no per-row index arithmetic);
 //   * horizontal neighbours come from an 8-row shared-memory ring of t and 2-row rings of A11 and f = A12 * D_eta t;
 //   * every operand is read from global memory once per point: one elected thread issues a bulk-TMA copy of the strip's
 //     row of every field (1 KiB each, completion counted on an mbarrier) into a 4-stage shared-memory ring two rows ahead of
@@ -112,7 +114,23 @@ struct MarchArgs {
                   // 4 = no output phase (staging only), 6 = no operand fetch (compute only); results are then wrong
 };
 
-template <int MODE, bool HAS_V>
+// pma2_rhs_point (mesh_math.h) with the regularisation term (two pow calls, ~200 instructions, epsilon = 0 in PMA2_nk.py's
+// runs) kept OUT of the unrolled row loop: same operations in the same order.
+__device__ __noinline__ double march_pma2_eps_term(double lambd, double epsilon, int m, double q) {
+  return lambd * pow(epsilon, (double)(m - 2)) / pow(q, (double)m);
+}
+__device__ __forceinline__ double march_pma2_rhs(const Pma2Params& p, double u, double lap2) {
+  const double q = 1.0 + u;
+  double rhs = -p.lambd / (q * q);
+  if (p.epsilon != 0.0) rhs += march_pma2_eps_term(p.lambd, p.epsilon, p.m, q);
+  rhs -= p.beta * p.beta * lap2;
+  return rhs;
+}
+
+// TMA (compile time): operand rows by bulk-TMA copies (one elected thread) / by one 8-byte cp.async per thread and field.  A
+// template parameter rather than a run-time flag: the row loop is unrolled 8x and carried both fetch paths in every copy of
+// its body (ncu: 16 % of the warp stalls were instruction-cache misses, `stall_no_inst`).
+template <int MODE, bool HAS_V, bool TMA>
 __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_kernel(const __grid_constant__ MarchArgs A, double* S,
                                                                        ReduceWs ws) {
   if (A.skippable && S[JS_STOP] != 0.0) return;
@@ -140,7 +158,7 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
       A.out[e] = lap;
       if (A.out2) A.out2[e] = tc;
     } else {
-      double rhs = bdy ? 0.0 : pma2_rhs_point(A.pp, u, lap);
+      double rhs = bdy ? 0.0 : march_pma2_rhs(A.pp, u, lap);
       double F = (u - uval) * inv_dt - (rhs + cn) * 0.5; // pma2_combine_point with 1/dt rounded once
       if (MODE == MARCH_PMA2_RESID) {
         A.out[e] = F;
@@ -193,7 +211,7 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
     const int strip = id % A.nstrips, chunk = id / A.nstrips;
     const int r0 = 4 + chunk * A.rows_per_chunk;
     const int r1 = min(ny - 4, r0 + A.rows_per_chunk);
-    const bool tma = A.tma != 0;
+    constexpr bool tma = TMA;
     const int halo = march_halo(tma), outw = march_out(tma);
     const int c_strip = 4 + strip * outw - halo; // first column of the strip (even with bulk-TMA fetch)
     const int c_raw = c_strip + tid;
@@ -215,11 +233,16 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
     const double wy0 = g.c1y[0], wy1 = g.c1y[1], wy3 = g.c1y[3], wy4 = g.c1y[4];
     // (the centred first-derivative weight of the point itself is 0 and is left out of the sums)
 
-    // Register windows as circular buffers of period 7 (the row loop is unrolled 7x, so every index below is a
-    // compile-time constant and no register is ever moved): with m counted from the first warm-up row,
-    //   tw[m % 7]           = t(r0 - 3 + m, c)   rows r-3..r+3 of output row r = r0 + u are slots (u + k + 3) % 7
-    //   a22w[m % 7], gw[..] = A22, g (r0 - 2 + m, c)   rows r-2..r+2 are slots (u + k + 2) % 7
-    double tw[7], a22w[7], gw[7];
+    // Register windows as circular buffers of period 8 (the row loop is unrolled 8x, so every index below is a
+    // compile-time constant and no register is ever moved; only the live rows hold registers): with m counted from the
+    // first warm-up row,
+    //   tw[m % 8]           = t(r0 - 3 + m, c)   rows r-3..r+3 of output row r = r0 + 8 it + u are slots (u + k + 3) % 8
+    //   a22w[m % 8], gw[..] = A22, g (r0 - 2 + m, c)   rows r-2..r+2 are slots (u + k + 2) % 8
+    // The shared-memory rings use the same relative row count: row r + k of t is Ts[(u + k + 3) % 8], the operand stage of
+    // row r is u % stages, the A11 / f slot u % 2 -- every shared-memory address of the loop body is base + immediate.
+    constexpr int PER = 8;
+    static_assert(kMarchRing == PER, "the t ring and the register windows share the period");
+    double tw[PER], a22w[PER], gw[PER];
     double a12_0 = 0.0, a12_1 = 0.0, a12_2 = 0.0;
     const double rx = __drcp_rn(288 * g.dksi2), ry = __drcp_rn(288 * g.deta2); // one rounding each, instead of a
                                                                               // division per point and direction
@@ -232,12 +255,13 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
     // the refilled stage was last read before the barrier of iteration r-1 (its post-barrier operands J, u, uval, cn, f0
     // included); issued after the barrier of iteration r (JFNK_MARCH_LATE, ahead + 1 stages) it is the stage of row r-1.
     const uint32_t row_bytes = (uint32_t)(min(kMarchThreads, nx - c_strip) * 8);
-    auto issue = [&](int r) {
+    // qrel = (r - r0) mod 8, a compile-time constant at every call site
+    auto issue = [&](int r, int qrel) {
       if (tma) {
         // (the issuing lane rotates over the warps: ~30 instructions per row that would otherwise make warp 0 the last to
         //  reach every row barrier)
-        if (tid == ((r & (kMarchThreads / 32 - 1)) << 5) && r < r1 && A.debug_skip != 6) {
-          const int stg = (r - r0) % kMarchStages;
+        if (tid == ((qrel & (kMarchThreads / 32 - 1)) << 5) && r < r1 && A.debug_skip != 6) {
+          const int stg = (PER % kMarchStages == 0) ? qrel % kMarchStages : (r - r0) % kMarchStages;
           double* pf = Pf + (size_t)stg * NF * kMarchThreads;
           uint64_t* bar = &full[stg];
           const size_t o3 = (size_t)(r + 3) * nx + c_strip, o2 = (size_t)(r + 2) * nx + c_strip, o0 = (size_t)r * nx + c_strip;
@@ -261,7 +285,7 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
         return;
       }
       if (r < r1 && A.debug_skip != 6) {
-        double* pf = Pf + (size_t)((r - r0) % (kMarchAheadCp + 1)) * NF * kMarchThreads + tid;
+        double* pf = Pf + (size_t)(qrel % (kMarchAheadCp + 1)) * NF * kMarchThreads + tid;
         const size_t o3 = (size_t)(r + 3) * nx + c, o2 = (size_t)(r + 2) * nx + c, o0 = (size_t)r * nx + c;
         cp_async8(pf + MF_X * kMarchThreads, A.x + o3);
         if (HAS_V) cp_async8(pf + MF_V * kMarchThreads, A.v + o3);
@@ -279,8 +303,9 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
       }
       cp_async_commit(); // (an empty group past the last row keeps the group count uniform)
     };
-    const int ahead = tma ? kMarchAhead : kMarchAheadCp;
-    for (int k = 0; k < ahead; ++k) issue(r0 + k); // (before the warm-up, so that the first rows land behind it)
+    constexpr int ahead = tma ? kMarchAhead : kMarchAheadCp;
+#pragma unroll
+    for (int k = 0; k < ahead; ++k) issue(r0 + k, k); // (before the warm-up, so that the first rows land behind it)
 
     // warm-up: rows r0-3 .. r0+2 of t ; g and A22 of rows r0-2 .. r0+1.  All global loads are issued before the first use and
     // the six rows go into the ring behind ONE barrier (a load -> store -> barrier chain per row cost six serial memory
@@ -299,11 +324,11 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
         }
       }
 #pragma unroll
-      for (int m = 0; m < 6; ++m) Ts[(r0 - 3 + m) & (kMarchRing - 1)][st] = tw[m];
+      for (int m = 0; m < 6; ++m) Ts[m][st] = tw[m];
       __syncthreads();
 #pragma unroll
       for (int m = 1; m <= 4; ++m) {
-        const double* T = Ts[(r0 - 3 + m) & (kMarchRing - 1)] + st;
+        const double* T = Ts[m] + st;
         const double vk = wx0 * T[-2] + wx1 * T[-1] + wx3 * T[1] + wx4 * T[2];
         gw[m - 1] = wa12[m - 1] * vk;
       }
@@ -316,42 +341,48 @@ __global__ void __launch_bounds__(kMarchThreads, JFNK_MARCH_MINCTAS) mesh_march_
     double py_0 = a22w[2] * (tw[1] - 8 * tw[2] + 8 * tw[4] - tw[5]);
     double hy_m = (-a22w[0] + 9 * a22w[1] + 9 * a22w[2] - a22w[3]) * (tw[1] - 27 * tw[2] + 27 * tw[3] - tw[4]);
 #endif
-    for (int rb = r0; rb < r1; rb += 7) {
+    constexpr bool kStagesDivide = (PER % kMarchStages == 0);
+    const double* const pf0 = Pf + tid;
+    for (int rb = r0; rb < r1; rb += PER) {
 #pragma unroll
-      for (int u = 0; u < 7; ++u) {
+      for (int u = 0; u < PER; ++u) {
         const int r = rb + u;
         if (r >= r1) break;
-        if (!JFNK_MARCH_LATE || !tma) issue(r + ahead);
-        const int q = r - r0;
+        if (!JFNK_MARCH_LATE || !tma) issue(r + ahead, (u + ahead) % PER);
+        const int q = r - r0; // = 8 it + u
+        const int stg = tma ? (kStagesDivide ? u % kMarchStages : q % kMarchStages) : u % (kMarchAheadCp + 1);
         if (tma) {
-          if (A.debug_skip != 6) mbar_wait(&full[q % kMarchStages], (uint32_t)((q / kMarchStages) & 1)); // row r has landed
+          // (with 2 or 4 stages the phase of stage u % stages in period it is a constant as well)
+          const uint32_t par = (kStagesDivide && (PER / kMarchStages) % 2 == 0) ? (uint32_t)((u / kMarchStages) & 1)
+                                                                                : (uint32_t)((q / kMarchStages) & 1);
+          if (A.debug_skip != 6) mbar_wait(&full[stg], par); // row r has landed
         } else cp_async_wait<kMarchAheadCp>(); // the group of row r has landed
-        const double* pf = Pf + (size_t)(tma ? q % kMarchStages : q % (kMarchAheadCp + 1)) * NF * kMarchThreads + tid;
+        const double* pf = pf0 + (size_t)stg * NF * kMarchThreads;
         const double tnew = HAS_V ? combine(pf[MF_X * kMarchThreads], a, pf[MF_V * kMarchThreads]) : pf[MF_X * kMarchThreads];
-        tw[(u + 6) % 7] = tnew;
-        a22w[(u + 4) % 7] = pf[MF_A22 * kMarchThreads];
+        tw[(u + 6) % PER] = tnew;
+        a22w[(u + 4) % PER] = pf[MF_A22 * kMarchThreads];
         a12_0 = a12_1; a12_1 = a12_2; a12_2 = pf[MF_A12N * kMarchThreads]; // A12 of rows r, r+1, r+2
         const double a12r2 = a12_2, a12r = a12_0, a11 = pf[MF_A11 * kMarchThreads];
 
-        const int slot = r & 1;
-        Ts[(r + 3) & (kMarchRing - 1)][st] = tnew;
+        const int slot = u & 1;
+        Ts[(u + 6) % PER][st] = tnew; // row r + 3
         A11s[slot][st] = a11;
-#define TW(k) tw[(u + (k) + 3) % 7]
-#define AY(k) a22w[(u + (k) + 2) % 7]
-#define GW(k) gw[(u + (k) + 2) % 7]
+#define TW(k) tw[(u + (k) + 3) % PER]
+#define AY(k) a22w[(u + (k) + 2) % PER]
+#define GW(k) gw[(u + (k) + 2) % PER]
         // D_eta t at (r, c) from the register window ; f = A12 D_eta t
         const double ve = wy0 * TW(-2) + wy1 * TW(-1) + wy3 * TW(1) + wy4 * TW(2);
         Fs[slot][st] = a12r * ve;
         {
           // D_ksi t at (r+2, c) from the row staged one iteration ago ; g = A12 D_ksi t
-          const double* T2 = Ts[(r + 2) & (kMarchRing - 1)] + st;
+          const double* T2 = Ts[(u + 5) % PER] + st;
           const double vk = wx0 * T2[-2] + wx1 * T2[-1] + wx3 * T2[1] + wx4 * T2[2];
           GW(2) = a12r2 * vk;
         }
         if (A.debug_skip != 3 || tma) __syncthreads(); // (the bulk-TMA ring relies on this barrier for its slot reuse)
-        if (JFNK_MARCH_LATE && tma) issue(r + ahead);  // refills the stage of row r-1: every thread is past iteration r-1
+        if (JFNK_MARCH_LATE && tma) issue(r + ahead, (u + ahead) % PER);  // refills the stage of row r-1: every thread is past iteration r-1
         if (is_out && A.debug_skip != 4) {
-          const double* T = Ts[r & (kMarchRing - 1)] + st;
+          const double* T = Ts[(u + 3) % PER] + st;
           const double* AX = A11s[slot] + st;
           const double* FX = Fs[slot] + st;
           const double xx = (4 * (AX[-1] * (T[-3] - 8 * T[-2] + 8 * T[0] - T[1])) -
