@@ -134,6 +134,17 @@ def main():
                          f"way: {sec:.3f} s/step at {fev:.0f} residual evaluations/step; normalised per evaluation and per grid "
                          f"point and extrapolated to {N}^2 at {fe:.0f} evaluations/step (EXTRAPOLATED, not run at this size)",
                "measured_seconds_per_step_on_sample": sec}
+    # DRAM traffic per launch of the dominant class from the committed ncu --set full capture (2048^2 only): the marching class
+    # alternates its two passes, so the figure is the mean of the two kernels' dram read + write bytes
+    traffic, traffic_src = None, None
+    tj = os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")
+    if dom[0] == "mesh_march" and N == 2048 and os.path.exists(tj):
+        t = json.load(open(tj))
+        if "mesh_march_lap" in t and "mesh_march_pma2_jvp" in t:
+            traffic = 0.5 * (t["mesh_march_lap"]["dram_bytes"] + t["mesh_march_pma2_jvp"]["dram_bytes"])
+            alg = 0.5 * (t["mesh_march_lap"]["algorithmic_bytes"] + t["mesh_march_pma2_jvp"]["algorithmic_bytes"])
+            traffic_src = (f"ncu --set full, mean of the Lap pass and the PMA2 pass (profiles/ncu_traffic_r2.json): "
+                           f"dram read+write = {traffic / alg:.3f} x algorithmic")
     summary = {"metric": f"PMA2_nk time-steps/s, synthetic {N}^2 fp64 (BASELINE config 3)", "value": len(timed) / total, "unit": "steps/s",
                "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed),
                "higher_is_better": True, "dtype": "f64", "data": "synthetic",
@@ -145,7 +156,8 @@ def main():
                "e2e": {"value": 1.0 / e2e_s, "unit": "steps/s", "call": "set_mesh/set_prev/newton_krylov/relax_mesh with host ndarrays",
                        "h2d_bytes_per_step": 8 * N * N * 5, "d2h_bytes_per_step": 8 * N * N * 2},
                "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                            "traffic": None, "note": "algorithmic bytes of the class (DESIGN.md) / CUDA-event time on the launch stream"},
+                            "traffic": traffic, "traffic_source": traffic_src,
+                            "note": "algorithmic bytes of the class (DESIGN.md) / CUDA-event time on the launch stream"},
                "cpu_baseline": cpu, "kernels": kernels}
     print(json.dumps(summary))
 

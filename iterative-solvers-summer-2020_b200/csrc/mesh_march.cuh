@@ -10,22 +10,24 @@
 //     addresses are immediates too (no per-row index arithmetic);
 //   * horizontal neighbours come from an 8-row shared-memory ring of t and 2-row rings of A11 and f = A12 * D_eta t;
 //   * every operand is read from global memory once per point: one elected thread issues a bulk-TMA copy of the strip's
-//     row of every field (1 KiB each, completion counted on an mbarrier) into a 4-stage shared-memory ring two rows ahead of
-//     its use; unaligned / odd grids fall back to one 8-byte cp.async per thread and field, one row ahead;
+//     row of every field (1 KiB each, completion counted on an mbarrier) into a 4-stage shared-memory ring three rows ahead
+//     of its use (requested after the row barrier, into the stage of the row just finished); unaligned / odd grids use one
+//     8-byte cp.async per thread and field, one row ahead (the fetch path is a template parameter);
 //   * the stencil input may be the combination t = x + a v (FD-JVP / line search), formed when a row is consumed;
 //   * divisions by 288 h^2, J, dt and the FD step are multiplications by a correctly rounded reciprocal.
 // One block barrier per row.  Only interior points (4 <= r < ny-4, 4 <= c < nx-4: no closure stencil in reach) are
 // marched; the frame of 4 rows / columns along each edge is done by a few extra CTAs of the same launch with the
 // general per-point formulas (mesh_laplace_general_g), reading t through the same accessor; they run concurrently
-// with the marching CTAs (33 us alone against ~90 us for the interior at 2048^2).
+// with the marching CTAs (33 us alone against ~65 us for the interior at 2048^2).
 //
 // Modes: MARCH_LAP        out = Lap t (out2 = t when non-null)
 //        MARCH_PMA2_RESID u = px + pa pv ; F = (u - uval)/dt - (rhs(u, Lap t) + cn)/2 ; out = F ; sum F^2, max|F|, max|u|
 //        MARCH_PMA2_JVP   out = (F - f0)/div
 // Algorithmic bytes per point: LAP 6 fields (t, A11, A22, A12, J in; out) + 1 with v; PMA2 pass 9-11 fields.
-// Measured on B200 at 2048^2 (ncu, profiles/ncu_march_r1.md): 3.2-3.4 TB/s of algorithmic traffic (0.5 of the
-// measured HBM peak; the one-thread-per-point kernels reach 0.24): DRAM traffic equals the algorithmic bytes; the limit
-// is the per-row dependency chain of fp64 operations at 16 resident warps per SM (stall reason "wait"), not a pipe.
+// Measured on B200 at 2048^2 (ncu, profiles/ncu_prof_marchp8b_2048_r2.md): 4.6 TB/s of algorithmic traffic
+// (0.70 of the measured HBM peak; round 1: 0.5, the one-thread-per-point kernels 0.24): DRAM traffic equals the algorithmic bytes;
+// the limit is the instruction stream of the row loop at 16 resident warps per SM (fixed-latency dependencies, the row barrier,
+// instruction fetch -- the loop body is kept small on purpose: 309 SASS instructions per row, see the notes at the template).
 #pragma once
 #include "cuda_common.cuh"
 #include "mesh_kernels.cuh"
