@@ -240,6 +240,31 @@ def test_pma2_marching_kernel_vs_point_kernel_and_oracle(cuda_buffers, N):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N", [1100, 1101])
+def test_pma2_marching_kernel_long_row_chunks(cuda_buffers, N):
+    """Row chunks of ~22 rows per CTA (the grids above give every CTA exactly one period of the 8x unrolled row loop): the
+    operand ring wraps several times per chunk, so the compile-time stage / mbarrier-phase indices of the bulk-TMA path
+    (N even) and the cp.async groups (N odd) are exercised across periods.  Residual and FD-JVP against the
+    one-thread-per-point kernels, tolerances as in the test above."""
+    Q, u, u0 = _pma2_state(N)
+    dt = 1e-4 * ((2.0 / (N - 1)) / 0.04) ** 4
+    Fm = jf.PMA2Residual(N=N, dt=dt, buffers=cuda_buffers)
+    Fp = jf.PMA2Residual(N=N, dt=dt, buffers=cuda_buffers, kernel_variant=1)
+    for F in (Fm, Fp):
+        F.set_mesh(Q)
+        F.set_prev(u0)
+    assert relmax(Fm(u), Fp(u)) < 1e-13
+    zero = np.zeros(N * N)
+    xi = np.linspace(-1, 1, N)
+    X, Y = np.meshgrid(xi, xi)
+    v = (np.sin(2 * X) * np.cos(Y) + 1e-6 * np.random.default_rng(5).standard_normal((N, N))).reshape(-1)
+    for F in (Fm, Fp):
+        F.set_prev(zero)
+        F.linearize(zero)
+    assert relmax(Fm.jvp(v), Fp.jvp(v)) < 1e-6
+
+
+@pytest.mark.gpu
 def test_droplet_marching_laplace_rectangular_grid(cuda_buffers):
     """MARCH_LAP with deriv_bc=1 on the 91 x 61 droplet grid (set_prev and the mesh relaxation use the summed
     Laplace_operator): goldens of the reference's own modules."""
