@@ -20,6 +20,13 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["vs_baseline"] is None
+    # both arms describe the same workload: the reference arm's `config` is the product arm's (the bounded CPU sample it
+    # actually timed is stated in cpu_baseline.sample)
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.workload_config(16384, 1)
+    assert "extrapolated" in d["cpu_baseline"]["sample"]
 
 
 def test_product_arm_fails_loudly_without_a_gpu():
