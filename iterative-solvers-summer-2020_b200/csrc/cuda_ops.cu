@@ -1079,9 +1079,16 @@ class CudaOps : public DeviceOps {
     pma_rhs_kernel<<<stream_grid(g_.n(), 256), 256, 0, stream_>>>(g_.n(), mon, J, add, alpha, S_, out);
   }
   void gemm(int M, int N, int K, const double* A, int ta, const double* B, int tb, double* C) {
-    dim3 grid((N + 15) / 16, (M + 15) / 16);
     Prof prof(this, K_MESH, 8.0 * ((double)M * K + (double)K * N + (double)M * N));
-    small_gemm_kernel<<<grid, 256, 0, stream_>>>(M, N, K, A, ta, B, tb, C);
+    // fp64 tensor cores (DMMA); JFNK_DMMA_GEMM=0 selects the CUDA-core kernel it replaced
+    static const bool cuda_cores = getenv("JFNK_DMMA_GEMM") && atoi(getenv("JFNK_DMMA_GEMM")) == 0;
+    if (cuda_cores) {
+      dim3 grid((N + 15) / 16, (M + 15) / 16);
+      small_gemm_kernel<<<grid, 256, 0, stream_>>>(M, N, K, A, ta, B, tb, C);
+    } else {
+      dim3 grid((N + 31) / 32, (M + 31) / 32);
+      dmma_gemm_kernel<<<grid, 256, 0, stream_>>>(M, N, K, A, ta, B, tb, C);
+    }
   }
   bool ensure_dct() {
     const int nx = g_.nx, ny = g_.ny;

@@ -101,6 +101,51 @@ __device__ __forceinline__ void dmma_tile(const double* A, int sam, int sak, con
   d1 = c1 + e1;
 }
 
+// C[M x N] = op(A) . op(B), row-major, op = transpose when the flag is set (the operand conventions of small_gemm_kernel), on the
+// fp64 tensor cores: the dense DCT-matrix products of the mesh update on grids that are neither small enough for the cluster
+// kernel above nor a power of two (dct_fft.cuh).  One CTA owns a 32 x 32 tile of C (8 warps x two 8 x 8 DMMA tiles), K advances
+// in steps of 32 staged in shared memory, zero-filled past the edges; the global reads run along the contiguous index of each
+// operand whichever way it is stored.
+__global__ void __launch_bounds__(256) dmma_gemm_kernel(int M, int N, int K, const double* __restrict__ A, int ta,
+                                                        const double* __restrict__ B, int tb, double* __restrict__ C) {
+  __shared__ double sa[32][33], sb[32][33]; // sa[m][k], sb[k][n]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = blockIdx.y * 32, col0 = blockIdx.x * 32;
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int e = tid; e < 1024; e += 256) {
+      const int hi = e >> 5, lo = e & 31; // lo runs along the contiguous index of the operand
+      {
+        const int m = ta ? lo : hi, k = ta ? hi : lo;
+        const int row = row0 + m, kk = k0 + k;
+        sa[m][k] = (row < M && kk < K) ? (ta ? A[(size_t)kk * M + row] : A[(size_t)row * K + kk]) : 0.0;
+      }
+      {
+        const int k = tb ? lo : hi, n = tb ? hi : lo;
+        const int col = col0 + n, kk = k0 + k;
+        sb[k][n] = (kk < K && col < N) ? (tb ? B[(size_t)col * K + kk] : B[(size_t)kk * N + col]) : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int tt = warp * 2 + j, m0 = (tt >> 2) * 8, n0 = (tt & 3) * 8;
+      double d0, d1;
+      dmma_tile(&sa[0][0], 33, 1, &sb[0][0], 33, 1, 32, 32, 32, m0, n0, d0, d1);
+      acc[j][0] += d0;
+      acc[j][1] += d1;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int tt = warp * 2 + j;
+    const int r = row0 + (tt >> 2) * 8 + (lane >> 2), c = col0 + (tt & 3) * 8 + 2 * (lane & 3);
+    if (r < M && c < N) C[(size_t)r * N + c] = acc[j][0];
+    if (r < M && c + 1 < N) C[(size_t)r * N + c + 1] = acc[j][1];
+  }
+}
+
 __global__ void __launch_bounds__(kBandThreads) pma_relax_band_kernel(const __grid_constant__ RelaxArgs A) {
   namespace cg = cooperative_groups;
   cg::cluster_group cl = cg::this_cluster(); // the whole grid is one cluster

@@ -426,6 +426,29 @@ def test_fft_dct_mesh_update_matches_scipy_fft(monkeypatch, N):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N", [300])
+def test_dense_dct_mesh_update_tensor_core_gemm(monkeypatch, N):
+    """Grids that are neither a power of two nor small enough for the cluster kernel transform with dense DCT-matrix
+    products; those run on the fp64 tensor cores (dmma_gemm_kernel: 32 x 32 tiles, edges zero-filled -- 300 = 9 x 32 + 12).
+    Against the oracle's scipy.fft path and against the CUDA-core kernel it replaced."""
+    xi = np.linspace(-1, 1, N)
+    X, Y = np.meshgrid(xi, xi)
+    Q = np.reshape(0.5 * X ** 2 + 0.5 * Y ** 2 + 0.01 * np.cos(np.pi * X) * np.cos(np.pi * Y), N * N)
+    U = np.reshape(-0.3 * np.exp(-4 * (X ** 2 + Y ** 2)), N * N)
+    po = PMA2Oracle(N=N)
+    po.set_mesh(Q)
+    po.Uval = U.copy()
+    Qdt = po.ops.solve_pma(po.monitor(), po.met["J"], po.alpha, po.gamma)
+    got = {}
+    for dmma in ("1", "0"):
+        monkeypatch.setenv("JFNK_DMMA_GEMM", dmma)
+        P = jf.PMA2Residual(N=N)
+        got[dmma] = P.relax_mesh(Q, U, 1e-4, loops=1) - Q
+        assert rel(got[dmma], 1e-4 * Qdt) < 1e-11, dmma
+    assert rel(got["1"], got["0"]) < 1e-12
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("grid", ["91x61", "61x61", "81x61", "91x41"])
 @pytest.mark.parametrize("gs,tau", [("cgs-ifneeded", 0.25), ("cgs2", 0.25)])
 def test_one_launch_droplet_cycle_matches_streaming_path(monkeypatch, grid, gs, tau):
